@@ -1,0 +1,79 @@
+// The opaque context behind msgpu_ctx*: owns every device buffer of one rank's block of micro
+// systems (the memory MicroSolver owns in the reference: solutions, righthandsides,
+// system_matrices — src/elliptic-elliptic/micro.h:95-171).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/msgpu.h"
+#include "expr_compile.h"
+#include "problem_programs.h"
+#include "kernels.h"
+
+namespace msgpu {
+
+enum Phase { PH_TABLES = 0, PH_MOMENTS, PH_GATHER, PH_CG, PH_COUPLING, PH_COUNT };
+enum FlagSlot { FLAG_JACOBIAN = 0, FLAG_COUNTER = 1, FLAG_CGFAIL = 2 };
+
+struct PendingTimer {
+  int phase;
+  cudaEvent_t a, b;
+};
+
+}  // namespace msgpu
+
+struct msgpu_ctx {
+  msgpu_desc desc{};
+  std::string err;
+  int device = 0;
+  int num_sms = 1;
+  cudaStream_t stream = nullptr;
+  int own_stream = 0;
+
+  // problem definition
+  int N = 0;
+  std::vector<double> xy;
+  msgpu::FnDef fn[MSGPU_FN_COUNT];
+  double scalars[MSGPU_MAX_SCALARS] = {0};
+  int n_scalars = 0;
+
+  // compiled expressions
+  msgpu::ProblemPrograms pp;
+
+  // mesh
+  msgpu::MeshDims md{};
+  std::vector<int> ref_to_internal;
+  std::vector<double> q_pt, q_wt;
+  int chunk = 1;
+
+  // device memory
+  double *d_xy = nullptr, *d_slots = nullptr, *d_T0 = nullptr, *d_T1 = nullptr;
+  double *d_coord0 = nullptr, *d_coord1 = nullptr, *d_qtab = nullptr, *d_q1pt = nullptr, *d_q1wt = nullptr;
+  double *d_cell = nullptr, *d_face = nullptr;
+  double *d_diag = nullptr, *d_b0 = nullptr, *d_jw = nullptr, *d_edge = nullptr, *d_bv = nullptr;
+  double *d_b = nullptr, *d_x = nullptr, *d_xold = nullptr, *d_u = nullptr, *d_w = nullptr;
+  double *d_c = nullptr, *d_res = nullptr, *d_err = nullptr;
+  double *d_mass = nullptr, *d_macro = nullptr, *d_lumped = nullptr;  // parabolic: shared mass stencil, lumped weights
+  int *d_iters = nullptr, *d_flags = nullptr;
+  size_t bytes_allocated = 0;
+
+  // state
+  int setup_done = 0, assembled = 0, tables_valid = 0;
+  double tables_time = 0.0;
+  std::vector<int> h_iters;
+  long long cg_iterations_total = 0;
+  int cg_variant = 0;
+
+  // measurement
+  int timing = 0;
+  std::vector<msgpu::PendingTimer> pending;
+  double phase_ms[msgpu::PH_COUNT] = {0};
+  long long launches = 0;
+
+  // multi-GPU
+  int comm_ready = 0, rank = 0, n_ranks = 1, n_total = 0, k_offset = 0;
+  void* nccl_comm = nullptr;
+  std::vector<int> rank_counts, rank_offsets;
+};

@@ -1,0 +1,104 @@
+// Host-side tables for FE_Q<2>(1) on a uniform square mesh of [-1,1]^2: Gauss points, the
+// per-quadrature-point basis products the moment kernels need, and the reference's DoF
+// numbering.
+//
+// Replaces what the reference gets from deal.II at micro.cpp:141-144 (FEValues + QGauss<2>(12)),
+// bio micro.cpp:12-15 (FEFaceValues + QGauss<1>(12)), micro.cpp:41-42 / bio micro.cpp:74
+// (mesh generation) and micro.cpp:48 (distribute_dofs).
+//
+// Device ordering: node (ix,iy) -> r = ix*m + iy and cell (cx,cy) -> c = cx*nc + cy, i.e. the
+// y index runs fastest.  With the 32 lanes of a warp on consecutive cy, everything that
+// depends on (cx, qx) only is warp-uniform and everything that depends on (cy, qy) is
+// unit-stride in memory.
+#pragma once
+#include <cmath>
+#include <stdexcept>
+#include <vector>
+
+#include "kernels.h"
+
+namespace msgpu {
+
+// n-point Gauss-Legendre rule mapped to [0,1]; nodes ascending.
+inline void gauss_legendre_unit(int n, std::vector<double>& nodes, std::vector<double>& weights) {
+  nodes.resize(n);
+  weights.resize(n);
+  const long double PI = 3.14159265358979323846264338327950288L;
+  for (int k = 0; k < n; ++k) {
+    // Chebyshev-like start, then Newton on P_n
+    long double x = -cosl(PI * (4 * k + 3) / (4 * n + 2));
+    long double dp = 1;
+    for (int iter = 0; iter < 64; ++iter) {
+      long double pm1 = 1.0L, p = x;  // P_0, P_1
+      for (int j = 2; j <= n; ++j) {
+        long double pn = ((2 * j - 1) * x * p - (j - 1) * pm1) / j;
+        pm1 = p;
+        p = pn;
+      }
+      if (n == 0) p = 1.0L;
+      dp = n * (x * p - pm1) / (x * x - 1.0L);
+      long double dx = p / dp;
+      x -= dx;
+      if (fabsl(dx) < 1e-20L) break;
+    }
+    nodes[k] = static_cast<double>(0.5L * (x + 1.0L));
+    weights[k] = static_cast<double>(1.0L / ((1.0L - x * x) * dp * dp));
+  }
+}
+
+// Per volume quadrature point (qy*q + qx), premultiplied by the unit-cell weight w = w_qx*w_qy:
+//   [0..2]  eb^2, eb*e, e^2      (e = eta, eb = 1-eta)   -> d/dxi   * d/dxi   products
+//   [3..5]  xb^2, xb*x, x^2      (x = xi,  xb = 1-xi)    -> d/deta  * d/deta  products
+//   [6..9]  eb*xb, eb*x, e*xb, e*x                       -> d/dxi   * d/deta  products
+//   [10..13] shape values phi_0..phi_3 (deal.II vertex order (0,0),(1,0),(0,1),(1,1))
+inline std::vector<double> build_qtab(int q, const std::vector<double>& pt, const std::vector<double>& wt) {
+  std::vector<double> t(static_cast<size_t>(q) * q * QTAB_STRIDE);
+  for (int qy = 0; qy < q; ++qy)
+    for (int qx = 0; qx < q; ++qx) {
+      double x = pt[qx], e = pt[qy], xb = 1 - x, eb = 1 - e, w = wt[qx] * wt[qy];
+      double* r = &t[(static_cast<size_t>(qy) * q + qx) * QTAB_STRIDE];
+      r[0] = w * (eb * eb); r[1] = w * (eb * e); r[2] = w * (e * e);
+      r[3] = w * (xb * xb); r[4] = w * (xb * x); r[5] = w * (x * x);
+      r[6] = w * (eb * xb); r[7] = w * (eb * x); r[8] = w * (e * xb); r[9] = w * (e * x);
+      r[10] = w * (xb * eb); r[11] = w * (x * eb); r[12] = w * (xb * e); r[13] = w * (x * e);
+    }
+  return t;
+}
+
+// Reference DoF numbering of FE_Q(1): DoFs are numbered in the order the active cells first
+// touch their vertices, local vertex order (0,0),(1,0),(0,1),(1,1).  Active cells of
+// hyper_cube+refine_global come in Morton order (child index = cx_bit + 2*cy_bit per level),
+// those of subdivided_hyper_cube row by row with x fastest.
+// Returns ref_to_internal[ref dof] = ix*m + iy.
+inline std::vector<int> reference_numbering(int mesh_kind, int nc) {
+  const int m = nc + 1;
+  std::vector<int> internal_to_ref(static_cast<size_t>(m) * m, -1);
+  int levels = 0;
+  if (mesh_kind == 0) {
+    while ((1 << levels) < nc) ++levels;
+    if ((1 << levels) != nc) throw std::runtime_error("refine_global meshes have 2^r cells per axis");
+  }
+  int next = 0;
+  for (int a = 0; a < nc * nc; ++a) {
+    int cx, cy;
+    if (mesh_kind == 0) {
+      cx = cy = 0;
+      for (int bit = 0; bit < levels; ++bit) {
+        cx |= ((a >> (2 * bit)) & 1) << bit;
+        cy |= ((a >> (2 * bit + 1)) & 1) << bit;
+      }
+    } else {
+      cx = a % nc;
+      cy = a / nc;
+    }
+    for (int v = 0; v < 4; ++v) {
+      int r = (cx + (v & 1)) * m + (cy + (v >> 1));
+      if (internal_to_ref[r] < 0) internal_to_ref[r] = next++;
+    }
+  }
+  std::vector<int> ref_to_internal(static_cast<size_t>(m) * m);
+  for (int r = 0; r < m * m; ++r) ref_to_internal[internal_to_ref[r]] = r;
+  return ref_to_internal;
+}
+
+}  // namespace msgpu

@@ -1,0 +1,128 @@
+// Launchers of the sm_100a kernels of libmsgpu.  Host code in
+// msgpu.cu calls these; each launcher returns the number of kernels it launched.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "vm_ops.h"
+
+namespace msgpu {
+
+// Geometry shared by all kernels.  Device ordering: node r = ix*m + iy, cell c = cx*nc + cy.
+struct MeshDims {
+  int nc;      // cells per axis
+  int m;       // nodes per axis
+  int n;       // m*m
+  int ld;      // leading dimension of the stored diagonals: n rounded up to even (16-byte rows for bulk copies)
+  int ncells;  // nc*nc
+  int q;       // Gauss points per direction
+  int P;       // 1-D evaluation points per system: nc*q quadrature abscissae, then m vertices
+  double h;    // cell side
+};
+
+// Per-context tables produced by the slot / line kernels.
+struct Tables {
+  const double* slots;  // [N][n_slots]
+  const double* T0;     // [N][n0][P]   y0-dependent nodes, point index p0 = cx*q + qx | nc*q + vertex
+  const double* T1;     // [N][n1][P]   y1-dependent nodes, point index p1 = qy*nc + cy | nc*q + vertex
+  int n_slots, n0, n1;
+};
+
+constexpr int CELL_STRIDE = 18;  // 10 local matrix entries, 4 load entries, 4 det-weighted basis integrals
+constexpr int FACE_STRIDE = 7;   // Robin mass (aa, ab, bb), load (a, b), stretch weights (a, b)
+constexpr int QTAB_STRIDE = 14; // see fe_tables.h build_qtab
+constexpr int NDIAG = 5;         // stored diagonals: offsets 0, +1, +m-1, +m, +m+1
+
+enum ProblemFlags : int {
+  PF_ELLIPTIC = 0,
+  PF_BIO = 1,
+  PF_PARABOLIC = 2
+};
+
+// K0 tables ---------------------------------------------------------------------------------
+int launch_slots(cudaStream_t s, const VmProgram& prog, const double* xy, int N, double t, double* slots, int n_slots);
+int launch_lines(cudaStream_t s, const VmProgram& prog0, const VmProgram& prog1, const double* coord0,
+                 const double* coord1, int P, int N, const double* slots, int n_slots, double* T0, int n0, double* T1,
+                 int n1);
+
+// K1 cell moments: for systems [k0, k0+nk) writes cell[(kl*CELL_STRIDE + e)*ncells + c].
+// Program outputs: F00 F01 F10 F11 G  (has_map) or just G (no mapping: F = identity).
+int launch_cell_moments(cudaStream_t s, const VmProgram& prog, MeshDims md, Tables tb, const double* qtab, int k0, int nk,
+                        double stiffness_scale, int has_map, double* cell, int* error_flag);
+
+// K1 faces: for systems [k0,k0+nk) and side in {0:x=-1, 1:x=+1, 2:y=-1, 3:y=+1} writes
+// face[((kl*4 + side)*FACE_STRIDE + e)*nc + f].  One program per side: outputs F00..F11, BC.
+int launch_face_moments(cudaStream_t s, const VmProgram& prog, int side, MeshDims md, Tables tb, const double* q1d_pt,
+                        const double* q1d_wt, int k0, int nk, int has_map, double* face);
+
+// K1 gather: cell (and face) arrays -> stencil diagonals + load vectors of systems [k0,k0+nk).
+struct GatherArgs {
+  MeshDims md;
+  int problem;
+  int k0, nk;
+  const double* cell;   // chunk-local
+  const double* face;   // chunk-local or null
+  double robin_left, robin_right;  // kappa_2, kappa_4 (bio)
+  double* diag;         // [N][NDIAG][ld]
+  double* b0;           // [N][n]   load that does not depend on the macro solution
+  double* jw;           // [N][n]   elliptic: int phi_i det(F)   (multiplies u_k; also the bulk-integral weights)
+  double* edge;         // [N][4][m] bio: left stretch weights, right stretch weights, left bc load, right bc load
+};
+int launch_gather(cudaStream_t s, const GatherArgs& a);
+
+// K2 Dirichlet data + elimination (elliptic) and right-hand-side finalisation (all problems).
+int launch_boundary_values(cudaStream_t s, const VmProgram& prog, MeshDims md, Tables tb, int N, double* bv);
+struct RhsArgs {
+  MeshDims md;
+  int problem;
+  int N;
+  const double* u;      // [N]
+  const double* w;      // [N] or null
+  double coef_u, coef_w;  // bio: kappa_1, kappa_3 ; elliptic: 1, 0
+  double* diag;
+  const double* b0;
+  const double* jw;
+  const double* edge;
+  const double* bv;     // [N][n] Dirichlet values (elliptic)
+  double* b;            // [N][n]
+  double* x;            // [N][n] start vector (elliptic: written; bio: untouched)
+};
+int launch_rhs_and_dirichlet(cudaStream_t s, const RhsArgs& a);
+
+// K4 batched CG --------------------------------------------------------------------------------
+struct CgArgs {
+  MeshDims md;
+  int N;
+  const double* diag;       // [N or 1][NDIAG][ld]
+  long long diag_stride;    // NDIAG*ld, or 0 when every system has the same matrix
+  const double* b;          // [N][n]
+  double* x;                // [N][n] in: start vector, out: solution
+  double tol;
+  int max_it;
+  int precond;
+  int* iters;               // [N]
+  double* res;              // [N]
+  int* work_counter;        // device int, zeroed by the launcher
+  int* fail_flag;           // device int: set to 1 if a system did not converge
+};
+// returns launches; *variant = 0 shared-memory resident, 1 global-memory
+int launch_cg(cudaStream_t s, const CgArgs& a, int num_sms, int* variant);
+
+// K5/K6 coupling integrals --------------------------------------------------------------------
+struct CouplingArgs {
+  MeshDims md;
+  int problem;
+  int N;
+  const double* x;
+  const double* jw;     // elliptic: [N][n]; parabolic: shared [n] lumped weights (stride 0)
+  long long jw_stride;
+  const double* edge;   // bio
+  double kappa_left, kappa_right;  // bio: kappa_2, kappa_4
+  double* c0;           // [N] (already offset to this rank's block)
+  double* c1;
+};
+int launch_coupling(cudaStream_t s, const CouplingArgs& a);
+
+// y = M x for the shared symmetric stencil matrix (parabolic K7 building block) ----------------
+int launch_shared_spmv(cudaStream_t s, MeshDims md, int N, const double* diag, const double* x, double* y);
+
+}  // namespace msgpu

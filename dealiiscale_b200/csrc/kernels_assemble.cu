@@ -1,0 +1,138 @@
+// Batched micro assembly on sm_100a: tables (K0), cell / face moments (K1), stencil gather,
+// Dirichlet elimination and right-hand sides (K2).
+//
+// Replaces, for all N micro systems at once,
+//   MicroSolver::compute_pullback_objects + integrate_cell + assemble_system
+//       (reference: src/elliptic-elliptic/micro.cpp:75-171)
+//   MicroSolver::local_assemble_system + copy_local_to_global
+//       (reference: src/bio-multiscale/micro.cpp:183-288)
+// The work is FP64-ALU bound (SURVEY.md §7 "Assembly is FP64-compute-heavy"); memory traffic is
+// the coalesced write of 18 doubles per cell and the read of the line tables, which are
+// warp-uniform (y0 side) or unit-stride (y1 side) by construction of the device ordering.
+#include <cstdio>
+
+#include "assemble_bodies.cuh"
+#include "kernels.h"
+
+namespace msgpu {
+
+namespace {
+
+constexpr int TB = 128;  // threads per block of the assembly kernels
+
+inline size_t vm_smem(const VmProgram& p, int threads) {
+  int regs = p.n_regs < 8 ? 8 : p.n_regs;
+  return static_cast<size_t>(regs) * threads * sizeof(double);
+}
+
+// Thin __global__ wrappers: thread id -> body.  TB threads per block, one VM register file of
+// n_regs doubles per thread in dynamic shared memory (register j of thread t at R[j*TB + t]).
+__global__ void __launch_bounds__(TB) k_slots(const __grid_constant__ VmProgram prog, const double* __restrict__ xy,
+                                               int N, double t, double* __restrict__ slots, int n_slots) {
+  extern __shared__ double R[];
+  body_slots(prog, xy, N, t, slots, n_slots, static_cast<long long>(blockIdx.x) * TB + threadIdx.x, R + threadIdx.x, TB);
+}
+__global__ void __launch_bounds__(TB) k_lines(const __grid_constant__ VmProgram prog0,
+                                               const __grid_constant__ VmProgram prog1,
+                                               const double* __restrict__ coord0, const double* __restrict__ coord1,
+                                               int P, int N, const double* __restrict__ slots, int n_slots,
+                                               double* __restrict__ T0, int n0, double* __restrict__ T1, int n1) {
+  extern __shared__ double R[];
+  body_lines(prog0, prog1, coord0, coord1, P, N, slots, n_slots, T0, n0, T1, n1,
+             static_cast<long long>(blockIdx.x) * TB + threadIdx.x, R + threadIdx.x, TB);
+}
+__global__ void __launch_bounds__(TB) k_cell_moments(const __grid_constant__ VmProgram prog, MeshDims md, Tables tb,
+                                                      const double* __restrict__ qtab, int k0, int nk,
+                                                      double stiffness_scale, int has_map,
+                                                      double* __restrict__ cell, int* __restrict__ error_flag) {
+  extern __shared__ double R[];
+  body_cell_moments(prog, md, tb, qtab, k0, nk, stiffness_scale, has_map, cell, error_flag,
+                    static_cast<long long>(blockIdx.x) * TB + threadIdx.x, R + threadIdx.x, TB);
+}
+__global__ void __launch_bounds__(TB) k_face_moments(const __grid_constant__ VmProgram prog, int side, MeshDims md,
+                                                      Tables tb, const double* __restrict__ q1d_pt,
+                                                      const double* __restrict__ q1d_wt, int k0, int nk, int has_map,
+                                                      double* __restrict__ face) {
+  extern __shared__ double R[];
+  body_face_moments(prog, side, md, tb, q1d_pt, q1d_wt, k0, nk, has_map, face,
+                    static_cast<long long>(blockIdx.x) * TB + threadIdx.x, R + threadIdx.x, TB);
+}
+__global__ void __launch_bounds__(TB) k_gather(GatherArgs a) {
+  body_gather(a, static_cast<long long>(blockIdx.x) * TB + threadIdx.x);
+}
+__global__ void __launch_bounds__(TB) k_boundary_values(const __grid_constant__ VmProgram prog, MeshDims md, Tables tb,
+                                                         int N, double* __restrict__ bv) {
+  extern __shared__ double R[];
+  body_boundary_values(prog, md, tb, N, bv, static_cast<long long>(blockIdx.x) * TB + threadIdx.x, R + threadIdx.x,
+                       TB);
+}
+__global__ void __launch_bounds__(TB) k_rhs(RhsArgs a) {
+  body_rhs(a, static_cast<long long>(blockIdx.x) * TB + threadIdx.x);
+}
+__global__ void __launch_bounds__(TB) k_mask_dirichlet(MeshDims md, int N, double* __restrict__ diag) {
+  body_mask_dirichlet(md, N, diag, static_cast<long long>(blockIdx.x) * TB + threadIdx.x);
+}
+
+inline int blocks_for(long long work) { return static_cast<int>((work + TB - 1) / TB); }
+
+}  // namespace
+
+int launch_slots(cudaStream_t s, const VmProgram& prog, const double* xy, int N, double t, double* slots, int n_slots) {
+  if (n_slots == 0 || N == 0) return 0;
+  k_slots<<<blocks_for(N), TB, vm_smem(prog, TB), s>>>(prog, xy, N, t, slots, n_slots);
+  return 1;
+}
+
+int launch_lines(cudaStream_t s, const VmProgram& prog0, const VmProgram& prog1, const double* coord0,
+                 const double* coord1, int P, int N, const double* slots, int n_slots, double* T0, int n0, double* T1,
+                 int n1) {
+  if ((n0 == 0 && n1 == 0) || N == 0) return 0;
+  size_t sm = vm_smem(prog0, TB);
+  size_t sm1 = vm_smem(prog1, TB);
+  if (sm1 > sm) sm = sm1;
+  k_lines<<<blocks_for(static_cast<long long>(N) * P), TB, sm, s>>>(prog0, prog1, coord0, coord1, P, N, slots, n_slots,
+                                                                     T0, n0, T1, n1);
+  return 1;
+}
+
+int launch_cell_moments(cudaStream_t s, const VmProgram& prog, MeshDims md, Tables tb, const double* qtab, int k0,
+                        int nk, double stiffness_scale, int has_map, double* cell, int* error_flag) {
+  if (nk == 0) return 0;
+  k_cell_moments<<<blocks_for(static_cast<long long>(nk) * md.ncells), TB, vm_smem(prog, TB), s>>>(
+      prog, md, tb, qtab, k0, nk, stiffness_scale, has_map, cell, error_flag);
+  return 1;
+}
+
+int launch_face_moments(cudaStream_t s, const VmProgram& prog, int side, MeshDims md, Tables tb, const double* q1d_pt,
+                        const double* q1d_wt, int k0, int nk, int has_map, double* face) {
+  if (nk == 0) return 0;
+  k_face_moments<<<blocks_for(static_cast<long long>(nk) * md.nc), TB, vm_smem(prog, TB), s>>>(
+      prog, side, md, tb, q1d_pt, q1d_wt, k0, nk, has_map, face);
+  return 1;
+}
+
+int launch_gather(cudaStream_t s, const GatherArgs& a) {
+  if (a.nk == 0) return 0;
+  k_gather<<<blocks_for(static_cast<long long>(a.nk) * a.md.n), TB, 0, s>>>(a);
+  return 1;
+}
+
+int launch_boundary_values(cudaStream_t s, const VmProgram& prog, MeshDims md, Tables tb, int N, double* bv) {
+  if (N == 0) return 0;
+  k_boundary_values<<<blocks_for(static_cast<long long>(N) * 4 * md.nc), TB, vm_smem(prog, TB), s>>>(prog, md, tb, N,
+                                                                                                   bv);
+  return 1;
+}
+
+int launch_rhs_and_dirichlet(cudaStream_t s, const RhsArgs& a) {
+  if (a.N == 0) return 0;
+  const int blocks = blocks_for(static_cast<long long>(a.N) * a.md.n);
+  k_rhs<<<blocks, TB, 0, s>>>(a);
+  if (a.problem == PF_ELLIPTIC) {
+    k_mask_dirichlet<<<blocks, TB, 0, s>>>(a.md, a.N, a.diag);
+    return 2;
+  }
+  return 1;
+}
+
+}  // namespace msgpu

@@ -1,0 +1,442 @@
+// Batched FP64 conjugate gradients on sm_100a (kernels K3/K4) and the coupling integrals (K5/K6).
+//
+// Replaces SolverCG<>::solve(A_k, x_k, b_k, PreconditionIdentity()) called once per micro system
+// (reference: src/elliptic-elliptic/micro.cpp:175-182, src/bio-multiscale/micro.cpp:309-314,
+// src/elliptic-parabolic/rho_solver.cpp:222-229) and the micro-reading loops of the macro solvers
+// (src/elliptic-elliptic/macro.cpp:134-166, src/bio-multiscale/macro.cpp:254-306,
+// src/elliptic-parabolic/pi_solver.cpp:178-197).
+//
+// Design (B200-first): one CTA owns one system at a time and keeps it ON CHIP for the whole
+// solve.  A Q1 system on a square mesh is a symmetric 9-point stencil, stored as 5 diagonals
+// (offsets 0, +1, +m-1, +m, +m+1 in the y-fastest node ordering).  For m <= 67 the 5 diagonals
+// plus the search direction d fit in the 227 KB of shared memory of one SM (206 KB at m = 65);
+// x, g and the thread's own d entries live in registers.  The matrix is therefore read from
+// HBM exactly once per solve instead of once per CG iteration, there are no column indices at
+// all, and every shared-memory access is unit-stride (row r = thread + i*blockDim).
+// CTAs pull systems from an atomic work counter, so different iteration counts balance out.
+//
+// The recurrence is deal.II 9.1's SolverCG: g = A x - b; d = -g; loop { h = A d;
+// alpha = gh/(d.h); x += alpha d; g += alpha h; res = |g|; stop if res <= tol;
+// beta = res^2/gh; d = beta d - g }.  Dot products use a fixed shuffle tree + fixed order over
+// warps, so results are bit-reproducible from run to run and independent of the SM.
+#include <cstdio>
+#include <cstdlib>
+
+#include "kernels.h"
+
+namespace msgpu {
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the CTA, result in every thread.  One barrier; `red` must not be reused before the
+// next barrier that follows this call (callers alternate between buffers).
+template <int BT>
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  constexpr int NW = BT / 32;
+  v = warp_sum(v);
+  if (NW == 1) return v;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double t = (lane < NW) ? red[lane] : 0.0;
+  return warp_sum(t);
+}
+
+// -------------------------------------------------------------------------------------------
+// Shared-memory resident CG.  BT threads, RPT rows per thread (BT*RPT >= n).
+template <int BT, int RPT, bool JACOBI>
+__global__ void __launch_bounds__(BT, 1) k_cg_resident(CgArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int s_k;
+  const int n = a.md.n, m = a.md.m, ld = a.md.ld;
+  const int pad = (m + 2) & ~1;          // even, >= m+1: zero guard in front of every diagonal
+  const int ms = pad + ld;               // stride between diagonals in shared memory
+  double* const mat = sm;                // [NDIAG][ms]
+  double* const dv = sm + NDIAG * ms + pad;   // dv[-pad .. n + pad)
+  double* const red = sm + NDIAG * ms + (n + 2 * pad);   // 3 x 32
+  const int tid = threadIdx.x;
+
+  // guards: zero once, never written again
+  for (int i = tid; i < NDIAG * ms; i += BT)
+    if ((i % ms) < pad || (i % ms) >= pad + n) mat[i] = 0.0;
+  for (int i = tid; i < pad; i += BT) {
+    dv[-pad + i] = 0.0;
+    dv[n + i] = 0.0;
+  }
+  const double* const M0 = mat + pad;
+  const double* const M1 = M0 + ms;
+  const double* const M2 = M1 + ms;
+  const double* const M3 = M2 + ms;
+  const double* const M4 = M3 + ms;
+  const int o2 = m - 1, o3 = m, o4 = m + 1;
+
+  auto spmv_row = [&](int r) -> double {
+    double s = M0[r] * dv[r];
+    s += M1[r] * dv[r + 1];
+    s += M1[r - 1] * dv[r - 1];
+    s += M2[r] * dv[r + o2];
+    s += M2[r - o2] * dv[r - o2];
+    s += M3[r] * dv[r + o3];
+    s += M3[r - o3] * dv[r - o3];
+    s += M4[r] * dv[r + o4];
+    s += M4[r - o4] * dv[r - o4];
+    return s;
+  };
+
+  for (;;) {
+    __syncthreads();  // everybody is done with the previous system (s_k, mat, dv)
+    if (tid == 0) s_k = atomicAdd(a.work_counter, 1);
+    __syncthreads();
+    const int k = s_k;
+    if (k >= a.N) break;
+
+    // ---- stage the matrix: HBM -> shared memory, once per solve
+    const double* dg = a.diag + static_cast<size_t>(k) * a.diag_stride;
+    for (int d = 0; d < NDIAG; ++d) {
+      const double* src = dg + static_cast<size_t>(d) * ld;
+      double* dst = mat + d * ms + pad;
+      for (int r = tid; r < n; r += BT) dst[r] = __ldg(src + r);
+    }
+    double xx[RPT], gg[RPT], dl[RPT];
+    const double* bk = a.b + static_cast<size_t>(k) * n;
+    double* xk = a.x + static_cast<size_t>(k) * n;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int r = tid + i * BT;
+      xx[i] = (r < n) ? xk[r] : 0.0;
+      if (r < n) dv[r] = xx[i];
+    }
+    __syncthreads();
+    // ---- g = A x - b
+    double part = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int r = tid + i * BT;
+      gg[i] = (r < n) ? (spmv_row(r) - bk[r]) : 0.0;
+      part += gg[i] * gg[i];
+    }
+    double res = sqrt(block_sum<BT>(part, red));
+    int it = 0;
+    bool ok = res <= a.tol;
+    double gh = 0.0;
+    if (!ok) {
+      __syncthreads();  // all rows of A x are done before d is overwritten
+      if (JACOBI) {
+        part = 0.0;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int r = tid + i * BT;
+          const double z = (r < n) ? gg[i] / M0[r] : 0.0;
+          dl[i] = -z;
+          part += gg[i] * z;
+          if (r < n) dv[r] = dl[i];
+        }
+        gh = block_sum<BT>(part, red + 32);
+      } else {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int r = tid + i * BT;
+          dl[i] = -gg[i];
+          if (r < n) dv[r] = dl[i];
+        }
+        gh = res * res;
+      }
+      for (;;) {
+        ++it;
+        __syncthreads();  // d complete
+        double hh[RPT];
+        part = 0.0;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int r = tid + i * BT;
+          hh[i] = (r < n) ? spmv_row(r) : 0.0;
+          part += dl[i] * hh[i];
+        }
+        const double alpha = gh / block_sum<BT>(part, red);
+        part = 0.0;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          xx[i] += alpha * dl[i];
+          gg[i] += alpha * hh[i];
+          part += gg[i] * gg[i];
+        }
+        res = sqrt(block_sum<BT>(part, red + 32));
+        if (res <= a.tol) {
+          ok = true;
+          break;
+        }
+        if (it >= a.max_it || res != res) break;
+        double beta = gh;
+        if (JACOBI) {
+          part = 0.0;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const int r = tid + i * BT;
+            hh[i] = (r < n) ? gg[i] / M0[r] : 0.0;
+            part += gg[i] * hh[i];
+          }
+          gh = block_sum<BT>(part, red + 64);
+          beta = gh / beta;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const int r = tid + i * BT;
+            dl[i] = beta * dl[i] - hh[i];
+            if (r < n) dv[r] = dl[i];
+          }
+        } else {
+          gh = res * res;
+          beta = gh / beta;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const int r = tid + i * BT;
+            dl[i] = beta * dl[i] - gg[i];
+            if (r < n) dv[r] = dl[i];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int r = tid + i * BT;
+      if (r < n) xk[r] = xx[i];
+    }
+    if (tid == 0) {
+      if (a.iters) a.iters[k] = it;
+      if (a.res) a.res[k] = res;
+      if (!ok) atomicExch(a.fail_flag, 1);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Global-memory CG for systems that do not fit in one SM's shared memory (m > 67): the matrix is
+// streamed from L2/HBM every iteration, work vectors live in a per-CTA workspace.  Same
+// recurrence, same reduction order; kept simple — the cluster/DSMEM variant is the next step.
+template <int BT>
+__global__ void __launch_bounds__(BT) k_cg_global(CgArgs a, double* __restrict__ workspace) {
+  __shared__ double red[96];
+  __shared__ int s_k;
+  const int n = a.md.n, m = a.md.m, ld = a.md.ld;
+  const int tid = threadIdx.x;
+  double* g = workspace + static_cast<size_t>(blockIdx.x) * 3 * n;
+  double* d = g + n;
+  double* h = d + n;
+  const int off[4] = {1, m - 1, m, m + 1};
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_k = atomicAdd(a.work_counter, 1);
+    __syncthreads();
+    const int k = s_k;
+    if (k >= a.N) break;
+    const double* dg = a.diag + static_cast<size_t>(k) * a.diag_stride;
+    const double* bk = a.b + static_cast<size_t>(k) * n;
+    double* xk = a.x + static_cast<size_t>(k) * n;
+    auto spmv = [&](const double* v, double* out) {
+      for (int r = tid; r < n; r += BT) {
+        double s = dg[r] * v[r];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double* dj = dg + static_cast<size_t>(j + 1) * ld;
+          if (r + off[j] < n) s += dj[r] * v[r + off[j]];
+          if (r - off[j] >= 0) s += dj[r - off[j]] * v[r - off[j]];
+        }
+        out[r] = s;
+      }
+    };
+    spmv(xk, h);
+    double part = 0.0;
+    for (int r = tid; r < n; r += BT) {
+      const double gr = h[r] - bk[r];
+      g[r] = gr;
+      part += gr * gr;
+    }
+    double res = sqrt(block_sum<BT>(part, red));
+    int it = 0;
+    bool ok = res <= a.tol;
+    if (!ok) {
+      double gh;
+      if (a.precond == 1) {
+        part = 0.0;
+        for (int r = tid; r < n; r += BT) {
+          const double z = g[r] / dg[r];
+          d[r] = -z;
+          part += g[r] * z;
+        }
+        gh = block_sum<BT>(part, red + 32);
+      } else {
+        for (int r = tid; r < n; r += BT) d[r] = -g[r];
+        gh = res * res;
+      }
+      for (;;) {
+        ++it;
+        __syncthreads();
+        spmv(d, h);
+        part = 0.0;
+        for (int r = tid; r < n; r += BT) part += d[r] * h[r];
+        const double alpha = gh / block_sum<BT>(part, red);
+        part = 0.0;
+        for (int r = tid; r < n; r += BT) {
+          xk[r] += alpha * d[r];
+          const double gr = g[r] + alpha * h[r];
+          g[r] = gr;
+          part += gr * gr;
+        }
+        res = sqrt(block_sum<BT>(part, red + 32));
+        if (res <= a.tol) {
+          ok = true;
+          break;
+        }
+        if (it >= a.max_it || res != res) break;
+        double beta = gh;
+        if (a.precond == 1) {
+          part = 0.0;
+          for (int r = tid; r < n; r += BT) {
+            const double z = g[r] / dg[r];
+            h[r] = z;
+            part += g[r] * z;
+          }
+          gh = block_sum<BT>(part, red + 64);
+          beta = gh / beta;
+          for (int r = tid; r < n; r += BT) d[r] = beta * d[r] - h[r];
+        } else {
+          gh = res * res;
+          beta = gh / beta;
+          for (int r = tid; r < n; r += BT) d[r] = beta * d[r] - g[r];
+        }
+      }
+    }
+    if (tid == 0) {
+      if (a.iters) a.iters[k] = it;
+      if (a.res) a.res[k] = res;
+      if (!ok) atomicExch(a.fail_flag, 1);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// K5/K6: one warp per system, segmented warp reduction.
+//   elliptic  c0 = sum_r x[r] * jw[r]                      = int v_k det(F) dy
+//   parabolic c0 = sum_r x[r] * jw[r] (shared lumped mass) = int rho_k dy
+//   bio       c0 = sum_left  (-kappa_2 x jL + bcL),  c1 = sum_right (-kappa_4 x jR + bcR)
+__global__ void __launch_bounds__(128) k_coupling(CouplingArgs a) {
+  const int warp = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= a.N) return;
+  const int k = warp;
+  const MeshDims& md = a.md;
+  const double* x = a.x + static_cast<size_t>(k) * md.n;
+  if (a.problem == PF_BIO) {
+    const double* edge = a.edge + static_cast<size_t>(k) * 4 * md.m;
+    double su = 0.0, sw = 0.0;
+    for (int iy = lane; iy < md.m; iy += 32) {
+      su += -a.kappa_left * x[iy] * edge[iy] + edge[2 * md.m + iy];
+      sw += -a.kappa_right * x[(md.m - 1) * md.m + iy] * edge[md.m + iy] + edge[3 * md.m + iy];
+    }
+    su = warp_sum(su);
+    sw = warp_sum(sw);
+    if (lane == 0) {
+      a.c0[k] = su;
+      a.c1[k] = sw;
+    }
+  } else {
+    const double* jw = a.jw + static_cast<size_t>(k) * a.jw_stride;
+    double s = 0.0;
+    for (int r = lane; r < md.n; r += 32) s += x[r] * jw[r];
+    s = warp_sum(s);
+    if (lane == 0) a.c0[k] = s;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_shared_spmv(MeshDims md, int N, const double* __restrict__ dg,
+                                                      const double* __restrict__ x, double* __restrict__ y) {
+  const long long t = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
+  if (t >= static_cast<long long>(N) * md.n) return;
+  const int k = static_cast<int>(t / md.n), r = static_cast<int>(t % md.n);
+  const double* v = x + static_cast<size_t>(k) * md.n;
+  const int off[4] = {1, md.m - 1, md.m, md.m + 1};
+  double s = dg[r] * v[r];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double* dj = dg + static_cast<size_t>(j + 1) * md.ld;
+    if (r + off[j] < md.n) s += dj[r] * v[r + off[j]];
+    if (r - off[j] >= 0) s += dj[r - off[j]] * v[r - off[j]];
+  }
+  y[t] = s;
+}
+
+size_t resident_smem_bytes(const MeshDims& md) {
+  const int pad = (md.m + 2) & ~1;
+  return (static_cast<size_t>(NDIAG) * (pad + md.ld) + md.n + 2 * pad + 96) * sizeof(double);
+}
+
+template <int BT, int RPT>
+int launch_resident(cudaStream_t s, const CgArgs& a, int num_sms) {
+  const size_t smem = resident_smem_bytes(a.md);
+  auto kern = a.precond == 1 ? k_cg_resident<BT, RPT, true> : k_cg_resident<BT, RPT, false>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem);
+  if (per_sm < 1) per_sm = 1;
+  long long grid = static_cast<long long>(num_sms) * per_sm;
+  if (grid > a.N) grid = a.N;
+  kern<<<static_cast<int>(grid), BT, smem, s>>>(a);
+  return 1;
+}
+
+double* g_workspace = nullptr;
+size_t g_workspace_bytes = 0;
+
+}  // namespace
+
+int launch_cg(cudaStream_t s, const CgArgs& a, int num_sms, int* variant) {
+  if (a.N == 0) return 0;
+  cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
+  cudaMemsetAsync(a.fail_flag, 0, sizeof(int), s);
+  const int n = a.md.n;
+  const bool fits = resident_smem_bytes(a.md) <= 227 * 1024;
+  const char* force = std::getenv("MSGPU_CG_VARIANT");  // "global" forces the streaming kernel (tests)
+  if (fits && !(force && force[0] == 'g')) {
+    if (variant) *variant = 0;
+    const char* wide = std::getenv("MSGPU_CG_WIDE");  // "1": 1024 threads x 5 rows instead of 512 x 9
+    if (n <= 32) return launch_resident<32, 1>(s, a, num_sms);
+    if (n <= 128) return launch_resident<128, 1>(s, a, num_sms);
+    if (n <= 384) return launch_resident<128, 3>(s, a, num_sms);
+    if (n <= 1280) return launch_resident<256, 5>(s, a, num_sms);
+    if (n <= 2560) return launch_resident<512, 5>(s, a, num_sms);
+    if (wide && wide[0] == '1') return launch_resident<1024, 5>(s, a, num_sms);
+    return launch_resident<512, 9>(s, a, num_sms);
+  }
+  if (variant) *variant = 1;
+  constexpr int BT = 512;
+  int grid = num_sms * 2;
+  if (grid > a.N) grid = a.N;
+  const size_t need = static_cast<size_t>(grid) * 3 * n * sizeof(double);
+  if (need > g_workspace_bytes) {
+    if (g_workspace) cudaFree(g_workspace);
+    if (cudaMalloc(&g_workspace, need) != cudaSuccess) return -1;
+    g_workspace_bytes = need;
+  }
+  k_cg_global<BT><<<grid, BT, 0, s>>>(a, g_workspace);
+  return 1;
+}
+
+int launch_coupling(cudaStream_t s, const CouplingArgs& a) {
+  if (a.N == 0) return 0;
+  const int blocks = (a.N * 32 + 127) / 128;
+  k_coupling<<<blocks, 128, 0, s>>>(a);
+  return 1;
+}
+
+int launch_shared_spmv(cudaStream_t s, MeshDims md, int N, const double* diag, const double* x, double* y) {
+  if (N == 0) return 0;
+  const long long work = static_cast<long long>(N) * md.n;
+  k_shared_spmv<<<static_cast<int>((work + 127) / 128), 128, 0, s>>>(md, N, diag, x, y);
+  return 1;
+}
+
+}  // namespace msgpu

@@ -1,0 +1,178 @@
+/* msgpu.h — C ABI of the B200 micro-problem engine (libmsgpu.so).
+ *
+ * Drop-in boundary for the batched micro path of 0mar/dealiiscale.  The reference has no
+ * FFI layer: Manager owns MacroSolver<2> and MicroSolver<2> by value and they exchange raw
+ * pointers (reference: src/elliptic-elliptic/manager.h:17-21, src/tools/pde_data.h:76-90).
+ * The boundary is therefore the public surface of MicroSolver / RhoSolver plus the
+ * micro-reading part of MacroSolver / PiSolver; every entry point below names the
+ * reference member it stands in for.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every host pointer is caller-owned and is copied
+ *     in / out synchronously (the call returns after the copy has completed);
+ *   - the context owns all device memory and one CUDA stream;
+ *   - every function returns an msgpu_status; no C++ exception crosses the boundary;
+ *     msgpu_last_error() gives the message of the last failure on that context;
+ *   - a context is used by one host thread at a time (as in the reference);
+ *   - micro systems ("grids") are numbered 0..N-1 in the order of the macro DoFs handed to
+ *     msgpu_set_grid_locations(); micro DoFs are exchanged in the REFERENCE numbering
+ *     (deal.II first-touch numbering of the chosen mesh kind), whatever the device layout is.
+ *   - there is no CPU fallback: without a CUDA device msgpu_create() fails.
+ */
+#ifndef MSGPU_H
+#define MSGPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct msgpu_ctx msgpu_ctx;
+
+typedef enum {
+  MSGPU_OK = 0,
+  MSGPU_ERR_INVALID = 1,        /* bad argument / call order                                   */
+  MSGPU_ERR_PARSE = 2,          /* expression cannot be parsed (mu::ParserError in the reference) */
+  MSGPU_ERR_JACOBIAN = 3,       /* det F <= 1e-4 somewhere (Assert in pde_data.cpp:182, mapping.cpp:20) */
+  MSGPU_ERR_NO_CONVERGENCE = 4, /* SolverControl::NoConvergence                                   */
+  MSGPU_ERR_CUDA = 5,
+  MSGPU_ERR_COMM = 6,
+  MSGPU_ERR_UNSUPPORTED = 7
+} msgpu_status;
+
+/* Which driver's micro problem. */
+typedef enum {
+  MSGPU_ELLIPTIC = 0,  /* src/elliptic-elliptic/micro.cpp : Dirichlet, matrix differs per grid      */
+  MSGPU_BIO = 1,       /* src/bio-multiscale/micro.cpp    : Robin left/right, Neumann top/bottom    */
+  MSGPU_PARABOLIC = 2  /* src/elliptic-parabolic/rho_solver.cpp : implicit Euler, one shared matrix */
+} msgpu_problem;
+
+typedef enum {
+  MSGPU_MESH_REFINE_GLOBAL = 0, /* hyper_cube(-1,1)+refine_global(r): Z-order cells (micro.cpp:40-44)   */
+  MSGPU_MESH_SUBDIVIDED = 1     /* subdivided_hyper_cube(n,-1,1): row-major cells (bio micro.cpp:74)     */
+} msgpu_mesh_kind;
+
+typedef struct {
+  int problem;        /* msgpu_problem                                                   */
+  int mesh_kind;      /* msgpu_mesh_kind                                                 */
+  int cells_per_axis; /* 2^refine_level or n_cells                                       */
+  int q_degree;       /* Gauss points per direction: 12 (elliptic, bio) or 2 (parabolic) */
+  int device;         /* CUDA device ordinal, -1 = current device                        */
+} msgpu_desc;
+
+/* Function slots of msgpu_set_function (the parsed functions of src/tools/pde_data.h). */
+typedef enum {
+  MSGPU_FN_MAPPING = 0,   /* "mapping"      2 components, zeta(x,y)                                 */
+  MSGPU_FN_JACOBIAN = 1,  /* "jac_mapping"  4 components, row-major F = grad_y zeta                 */
+  MSGPU_FN_RHS = 2,       /* micro_rhs | bulk_rhs_v | micro_rhs(t)                                  */
+  MSGPU_FN_BC = 3,        /* micro_bc (elliptic Dirichlet data, composed with the mapping)          */
+  MSGPU_FN_SOLUTION = 4,  /* micro_solution | solution_v (composed with the mapping, except parabolic) */
+  MSGPU_FN_BC_V1 = 5,     /* bio: inflow  (left,  y0=-1) | parabolic: micro_bc_robin               */
+  MSGPU_FN_BC_V2 = 6,     /* bio: outflow (right, y0=+1) | parabolic: micro_bc_neumann             */
+  MSGPU_FN_BC_V3 = 7,     /* bio: top     (y1=+1)                                                   */
+  MSGPU_FN_BC_V4 = 8,     /* bio: bottom  (y1=-1)                                                   */
+  MSGPU_FN_INIT = 9,      /* parabolic: init_rho                                                    */
+  MSGPU_FN_COUNT = 10
+} msgpu_function_slot;
+
+/* Scalar slots of msgpu_set_scalars.
+ *   bio       : kappa_1, kappa_2, kappa_3, kappa_4, D_2   (bio micro.cpp:186-190)
+ *   parabolic : kappa, p_F, R, D                          (rho_solver.cpp:127-130)            */
+#define MSGPU_MAX_SCALARS 8
+
+typedef enum { MSGPU_PRECOND_IDENTITY = 0, MSGPU_PRECOND_JACOBI = 1 } msgpu_precond;
+
+/* ---- life cycle: MicroSolver(data, refine_level) / ~MicroSolver ------------------------- */
+int msgpu_create(msgpu_ctx** ctx, const msgpu_desc* desc);
+void msgpu_destroy(msgpu_ctx* ctx);
+const char* msgpu_last_error(const msgpu_ctx* ctx);
+/* Run on a caller-provided cudaStream_t instead of the context's own stream (NULL = default stream). */
+int msgpu_set_stream(msgpu_ctx* ctx, void* cuda_stream);
+int msgpu_synchronize(msgpu_ctx* ctx);
+
+/* ---- MicroSolver::set_grid_locations (micro.cpp:242-245) --------------------------------
+ * xy[N][2]: the macro support points owned by this context (its shard of the macro DoFs). */
+int msgpu_set_grid_locations(msgpu_ctx* ctx, const double* xy, int n_grids);
+
+/* ---- MultiscaleData / BioData / TwoPressureData function initialisation ------------------
+ * (pde_data.cpp:25-35, :84-107, :144-158).  expr: ';'-separated components.  constants: the
+ * muParser constants the data class injects.  time_dependent: the variable list ends in ",t". */
+int msgpu_set_function(msgpu_ctx* ctx, int slot, const char* expr, const char* const* const_names,
+                       const double* const_values, int n_consts, int time_dependent);
+int msgpu_set_scalars(msgpu_ctx* ctx, const double* values, int n);
+
+/* ---- MicroSolver::setup (micro.cpp:32-37; bio :62-69; RhoSolver::setup rho_solver.cpp:28-32)
+ * Compiles the expressions, builds mesh tables, allocates N systems, evaluates the x- and
+ * line-dependent parts of the mapping (the dense equivalent of compute_pullback_objects). */
+int msgpu_setup(msgpu_ctx* ctx);
+
+int msgpu_num_grids(const msgpu_ctx* ctx);
+int msgpu_num_dofs(const msgpu_ctx* ctx);
+
+/* ---- MicroSolver::set_macro_solution (micro.cpp:97-100; bio :170-175; rho_solver.cpp:96-102)
+ * u[N] (elliptic: macro solution; bio: sol_u; parabolic: pi), w[N] (bio: sol_w) or NULL.
+ * The reference borrows a pointer and reads it at every run(); here the values are copied. */
+int msgpu_set_macro_solution(msgpu_ctx* ctx, const double* u, const double* w);
+
+/* ---- MicroSolver::assemble_system (micro.cpp:140-171) / bio local_assemble_system+copier
+ * (bio micro.cpp:183-298).  Kernels: line tables -> cell moments -> stencil gather (+ faces,
+ * + Dirichlet elimination).  Matrices, right-hand sides and start vectors stay on the device. */
+int msgpu_assemble(msgpu_ctx* ctx);
+
+/* ---- MicroSolver::solve (micro.cpp:175-182; bio :309-314): batched CG, deal.II recurrence,
+ * absolute tolerance on the recursive residual.  iters / final_res: [N] or NULL.
+ * Returns MSGPU_ERR_NO_CONVERGENCE if any system needs more than max_it steps. */
+int msgpu_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int precond, int* iters, double* final_res);
+
+/* ---- RhoSolver::iterate(dt) at time t (rho_solver.cpp:232-237): assemble, solve, old = new. */
+int msgpu_time_step(msgpu_ctx* ctx, double dt, double t, double abs_tol, int max_it, int* iters);
+
+/* ---- MacroSolver::compute_microscopic_contribution
+ * elliptic  c0[k] = int v_k J dy                      (macro.cpp:134-166)
+ * bio       c0[k], c1[k] = inflow / outflow integrals (bio macro.cpp:254-306)
+ * parabolic c0[k] = int rho_k dy                      (pi_solver.cpp:178-197)
+ * With a communicator (msgpu_comm_init) the arrays have n_total entries and are allgathered. */
+int msgpu_coupling(msgpu_ctx* ctx, double* c0, double* c1);
+
+/* ---- next tier: MicroSolver::compute_all_errors per-grid part (micro.cpp:189-205),
+ * bio get_residual (bio micro.cpp:368-378).  l2[N], h1[N] per grid; the macro-level
+ * aggregation (micro.cpp:206-214) is host work on N numbers. */
+int msgpu_errors(msgpu_ctx* ctx, double* l2, double* h1);
+int msgpu_residuals(msgpu_ctx* ctx, double* l2);
+
+/* ---- public data of MicroSolver: solutions (micro.h:97), in reference DoF numbering -------- */
+int msgpu_get_solutions(msgpu_ctx* ctx, int k0, int k1, double* out /* [k1-k0][n] */);
+int msgpu_set_solutions(msgpu_ctx* ctx, int k0, int k1, const double* in);
+int msgpu_get_rhs(msgpu_ctx* ctx, int k0, int k1, double* out /* [k1-k0][n] */);
+/* ref_to_internal[n]: position of reference DoF i in the device ordering. */
+int msgpu_get_dof_permutation(msgpu_ctx* ctx, int* ref_to_internal);
+/* support point of every reference DoF, xy[n][2] (DoFTools::map_dofs_to_support_points) */
+int msgpu_get_dof_points(msgpu_ctx* ctx, double* xy);
+/* System matrix of grid k as a dense n x n array in reference numbering (inspection / tests). */
+int msgpu_get_matrix_dense(msgpu_ctx* ctx, int k, double* out /* [n][n] */);
+
+/* ---- multi-GPU: one context per rank, contiguous blocks of macro DoFs per rank -------------
+ * (no reference call site: replaces the pointer hand-off of manager.cpp:25-26).
+ * id: 128 bytes from msgpu_comm_unique_id on rank 0, distributed by the caller. */
+int msgpu_comm_unique_id(char id[128]);
+int msgpu_comm_init(msgpu_ctx* ctx, const char id[128], int rank, int n_ranks, int n_total, int k_offset);
+/* Broadcast of the macro solution from root; every rank keeps its own block (set_macro_solution). */
+int msgpu_broadcast_macro(msgpu_ctx* ctx, double* u_all, double* w_all, int root);
+
+/* ---- measurement hooks ------------------------------------------------------------------- */
+typedef struct {
+  double ms_tables;    /* slot + line table kernels                    */
+  double ms_moments;   /* cell / face moment kernels                   */
+  double ms_gather;    /* stencil gather + boundary elimination        */
+  double ms_cg;        /* batched CG                                   */
+  double ms_coupling;  /* coupling integrals (+ collectives)           */
+  long long launches;  /* kernels launched by this context so far      */
+  long long cg_iterations_total; /* sum over systems of the last solve */
+  int cg_variant;      /* 0 = shared-memory resident, 1 = global-memory */
+} msgpu_stats;
+int msgpu_enable_timing(msgpu_ctx* ctx, int on);
+int msgpu_get_stats(msgpu_ctx* ctx, msgpu_stats* out, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSGPU_H */

@@ -246,8 +246,9 @@ struct MicroSolver {
           qpoint(c, q, y);
           data.map_jac.mtensor_value(grid_locations[k].data(), y, F);
           double det = F[0] * F[3] - F[1] * F[2];
-          // invert(F)
-          double inv[4] = {F[3] / det, -F[1] / det, -F[2] / det, F[0] / det};
+          // invert(F): deal.II multiplies the adjugate by 1/det
+          const double inv_det = 1.0 / det;
+          double inv[4] = {F[3] * inv_det, -F[1] * inv_det, -F[2] * inv_det, F[0] * inv_det};
           size_t t = table_index(k, c, q);
           det_jac[t] = det;
           // SymmetricTensor(inv * transpose(inv))

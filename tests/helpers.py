@@ -1,0 +1,279 @@
+"""ctypes bindings used by the tests only: the CPU oracle (oracle/_build/liboracle.so) and the
+CPU emulation harness of the product's per-thread kernel bodies (tests/native/_build/libemul.so).
+Neither is ever loaded by the product package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INPUT = os.path.join(ROOT, "input")
+
+# msgpu_function_slot
+FN_MAPPING, FN_JACOBIAN, FN_RHS, FN_BC, FN_SOLUTION, FN_BC_V1, FN_BC_V2, FN_BC_V3, FN_BC_V4, FN_INIT = range(10)
+ELLIPTIC, BIO, PARABOLIC = 0, 1, 2
+MESH_REFINE_GLOBAL, MESH_SUBDIVIDED = 0, 1
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def dptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def iptr(a):
+    return a.ctypes.data_as(_ip)
+
+
+def _build_if_missing(path, cmd, cwd):
+    if not os.path.exists(path):
+        subprocess.check_call(cmd, cwd=cwd, shell=True)
+    return path
+
+
+def load_oracle():
+    path = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+    _build_if_missing(path, "make -s", os.path.join(ROOT, "oracle"))
+    lib = C.CDLL(path)
+    lib.orc_last_error.restype = C.c_char_p
+    lib.orc_ell_create.restype = C.c_void_p
+    lib.orc_ell_create.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    for name in ("orc_bio_create",):
+        if hasattr(lib, name):
+            getattr(lib, name).restype = C.c_void_p
+    if hasattr(lib, "orc_par_create"):
+        lib.orc_par_create.restype = C.c_void_p
+    lib.orc_ell_time_micro.restype = C.c_double
+    return lib
+
+
+def load_emul():
+    path = os.path.join(ROOT, "tests", "native", "_build", "libemul.so")
+    _build_if_missing(path, "make -s", os.path.join(ROOT, "tests", "native"))
+    lib = C.CDLL(path)
+    lib.emul_create.restype = C.c_void_p
+    lib.emul_error.restype = C.c_char_p
+    lib.emul_error.argtypes = [C.c_void_p]
+    return lib
+
+
+def _const_arrays(constants):
+    names = [k.encode() for k in constants]
+    arr = (C.c_char_p * max(1, len(names)))(*names)
+    vals = np.array(list(constants.values()) or [0.0], dtype=np.float64)
+    return arr, vals, len(names)
+
+
+class Emul:
+    """The product's assembly bodies + compiler + VM, run sequentially on the CPU (tests only)."""
+
+    def __init__(self, problem, mesh_kind, nc, q):
+        self.lib = load_emul()
+        self.h = C.c_void_p(self.lib.emul_create(problem, mesh_kind, nc, q))
+        self.n = (nc + 1) ** 2
+        self.N = 0
+
+    def close(self):
+        if self.h:
+            self.lib.emul_destroy(self.h)
+            self.h = None
+
+    def set_function(self, slot, expr, constants=None, time_dependent=False):
+        arr, vals, n = _const_arrays(constants or {})
+        self.lib.emul_set_function(self.h, slot, expr.encode(), arr, dptr(vals), n, int(time_dependent))
+
+    def set_scalars(self, vals):
+        v = np.asarray(vals, dtype=np.float64)
+        self.lib.emul_set_scalars(self.h, dptr(v), len(v))
+
+    def setup(self, xy, t=0.0):
+        xy = np.ascontiguousarray(xy, dtype=np.float64)
+        self.N = xy.shape[0]
+        rc = self.lib.emul_setup(self.h, dptr(xy), self.N, C.c_double(t))
+        if rc:
+            raise RuntimeError(self.lib.emul_error(self.h).decode())
+
+    def assemble(self, u, w=None):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        w = np.ascontiguousarray(w if w is not None else np.zeros_like(u), dtype=np.float64)
+        return self.lib.emul_assemble(self.h, dptr(u), dptr(w))
+
+    def solve(self, tol, max_it):
+        its = np.zeros(self.N, dtype=np.int32)
+        rc = self.lib.emul_solve(self.h, C.c_double(tol), max_it, iptr(its))
+        return rc, its
+
+    def matrix(self, k):
+        out = np.zeros((self.n, self.n))
+        self.lib.emul_get_matrix_dense(self.h, k, dptr(out))
+        return out
+
+    def rhs(self, k):
+        out = np.zeros(self.n)
+        self.lib.emul_get_rhs(self.h, k, dptr(out))
+        return out
+
+    def solution(self, k):
+        out = np.zeros(self.n)
+        self.lib.emul_get_solution(self.h, k, dptr(out))
+        return out
+
+    def coupling(self):
+        c0 = np.zeros(self.N)
+        c1 = np.zeros(self.N)
+        self.lib.emul_coupling(self.h, dptr(c0), dptr(c1))
+        return c0, c1
+
+    def wrapped_nonzeros(self):
+        return self.lib.emul_check_wrapped_zeros(self.h)
+
+    def volume_point(self, k, cx, cy, qx, qy, n_out):
+        out = np.zeros(n_out)
+        self.lib.emul_eval_volume_point(self.h, k, cx, cy, qx, qy, dptr(out), n_out)
+        return out
+
+    def free_point(self, which, k, y0, y1):
+        out = C.c_double(0)
+        rc = self.lib.emul_eval_free_point(self.h, which, k, C.c_double(y0), C.c_double(y1), C.byref(out))
+        if rc:
+            raise RuntimeError("program not available")
+        return out.value
+
+    def stats(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self.lib.emul_program_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return a.value, b.value, c.value, d.value
+
+    def disassemble(self, which):
+        buf = C.create_string_buffer(1 << 16)
+        self.lib.emul_disassemble(self.h, which, buf, len(buf))
+        return buf.value.decode()
+
+
+def configure_elliptic(obj, data):
+    """Feed an EllipticData into anything with set_function (Emul or the product's MicroContext)."""
+    obj.set_function(FN_MAPPING, data.micro["mapping"], data.constants)
+    obj.set_function(FN_JACOBIAN, data.micro["jac_mapping"], data.constants)
+    obj.set_function(FN_RHS, data.micro["rhs"], data.constants)
+    obj.set_function(FN_BC, data.micro["bc"], data.constants)
+    obj.set_function(FN_SOLUTION, data.micro["solution"], data.constants)
+
+
+def configure_bio(obj, data):
+    obj.set_function(FN_MAPPING, data.micro["mapping"], data.constants)
+    obj.set_function(FN_JACOBIAN, data.micro["jac_mapping"], data.constants)
+    obj.set_function(FN_RHS, data.micro["rhs"], data.constants)
+    obj.set_function(FN_SOLUTION, data.micro["solution"], data.constants)
+    obj.set_function(FN_BC_V1, data.micro["bc_v_1"], data.constants)
+    obj.set_function(FN_BC_V2, data.micro["bc_v_2"], data.constants)
+    obj.set_function(FN_BC_V3, data.micro["bc_v_3"], data.constants)
+    obj.set_function(FN_BC_V4, data.micro["bc_v_4"], data.constants)
+    obj.set_scalars(data.scalars())
+
+
+def configure_parabolic(obj, data):
+    obj.set_function(FN_RHS, data.micro["rhs"], data.constants, True)
+    obj.set_function(FN_SOLUTION, data.micro["solution"], data.constants, True)
+    obj.set_function(FN_BC_V1, data.micro["bc_robin"], data.constants, True)
+    obj.set_function(FN_BC_V2, data.micro["bc_neumann"], data.constants, True)
+    obj.set_function(FN_INIT, data.micro["init_rho"], data.constants, False)
+    obj.set_scalars(data.scalars())
+
+
+class OracleElliptic:
+    def __init__(self, prm, macro_ref, micro_ref):
+        self.lib = load_oracle()
+        h = self.lib.orc_ell_create(os.path.join(INPUT, prm).encode() if not os.path.isabs(prm) else prm.encode(),
+                                    macro_ref, micro_ref)
+        if not h:
+            raise RuntimeError(self.lib.orc_last_error().decode())
+        self.h = C.c_void_p(h)
+        N, n = C.c_int(), C.c_int()
+        self.lib.orc_ell_sizes(self.h, C.byref(N), C.byref(n))
+        self.N, self.n = N.value, n.value
+
+    def close(self):
+        if self.h:
+            self.lib.orc_ell_destroy(self.h)
+            self.h = None
+
+    def grid_locations(self):
+        xy = np.zeros((self.N, 2))
+        self.lib.orc_ell_grid_locations(self.h, dptr(xy))
+        return xy
+
+    def dof_points(self):
+        xy = np.zeros((self.n, 2))
+        self.lib.orc_ell_dof_points(self.h, dptr(xy))
+        return xy
+
+    def micro_run(self, u, assemble_only=False):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        if self.lib.orc_ell_micro_run(self.h, dptr(u), int(assemble_only)) != 0:
+            raise RuntimeError(self.lib.orc_last_error().decode())
+
+    def matrix(self, k):
+        out = np.zeros((self.n, self.n))
+        self.lib.orc_ell_get_matrix_dense(self.h, k, dptr(out))
+        return out
+
+    def rhs(self, k):
+        out = np.zeros(self.n)
+        self.lib.orc_ell_get_rhs(self.h, k, dptr(out))
+        return out
+
+    def solution(self, k):
+        out = np.zeros(self.n)
+        self.lib.orc_ell_get_solution(self.h, k, dptr(out))
+        return out
+
+    def iters(self):
+        out = np.zeros(self.N, dtype=np.int32)
+        self.lib.orc_ell_get_iters(self.h, iptr(out))
+        return out
+
+    def bulk(self):
+        out = np.zeros(self.N)
+        self.lib.orc_ell_bulk(self.h, dptr(out))
+        return out
+
+    def grid_errors(self):
+        l2, h1 = np.zeros(self.N), np.zeros(self.N)
+        self.lib.orc_ell_grid_errors(self.h, dptr(l2), dptr(h1))
+        return l2, h1
+
+    def run(self, cycle_limit=-1):
+        r = self.lib.orc_ell_run(self.h, cycle_limit)
+        if r < 0:
+            raise RuntimeError(self.lib.orc_last_error().decode())
+        return r
+
+    def macro_dofs(self):
+        return self.lib.orc_ell_macro_dofs(self.h)
+
+    def history(self, cycle, solutions=True):
+        errs = np.zeros(4)
+        nm = self.macro_dofs()
+        macro = np.zeros(nm)
+        contrib = np.zeros(nm)
+        micro = np.zeros((self.N, self.n)) if solutions else None
+        its = np.zeros(self.N, dtype=np.int32)
+        mits = C.c_int()
+        self.lib.orc_ell_history(self.h, cycle, dptr(errs), dptr(macro), dptr(contrib),
+                                 dptr(micro) if solutions else None, iptr(its), C.byref(mits))
+        return dict(errors=errs, macro=macro, contribution=contrib, micro=micro, micro_iters=its, macro_iters=mits.value)
+
+    def table(self):
+        buf = C.create_string_buffer(1 << 16)
+        self.lib.orc_ell_table(self.h, buf, len(buf))
+        return buf.value.decode()
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
