@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the batched micro path (BASELINE.json metric: micro DoF-solves/s per fixed-point
+iteration; % of HBM roofline).
+
+One "step" = one fixed-point iteration of the micro path of `solve_biomath <prm> 6 6`
+(reference: src/bio-multiscale/micro.cpp:292-305 + macro.cpp:299-306): for every macro DoF owned
+by the rank, assemble the micro system (64x64 Q1 cells, QGauss(12)), solve it with CG from a zero
+start vector (abs. tol 1e-12, as the first cycle of the reference does), and compute the two
+micro->macro flux integrals; with N>1 ranks the integrals are allgathered and the macro solution
+is broadcast (NCCL).  Weak scaling: every GPU owns 65x65 = 4225 macro points.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/; deal.II is not
+installable here) on the host cores for the same metric on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "micro_dof_solves_per_s"
+UNIT = "DoF-solves/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--prm", default="biocase.prm")
+    ap.add_argument("--macro-ref", type=int, default=6, help="macro refinement: 2^r cells per axis per GPU")
+    ap.add_argument("--micro-ref", type=int, default=6, help="micro refinement: 2^r cells per axis")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="micro systems in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def macro_points(macro_cells: int, n_gpus: int):
+    """Macro support points: a (macro_cells+1) x (macro_cells+1) block per GPU, side by side in x0,
+    the whole lattice scaled into [-1,1]^2.  Row-major blocks so that every rank owns a contiguous
+    range of macro DoFs."""
+    m = macro_cells + 1
+    x1 = np.linspace(-1.0, 1.0, m)
+    x0 = np.linspace(-1.0, 1.0, m * n_gpus)
+    pts = []
+    for g in range(n_gpus):
+        for j in range(m):
+            for i in range(m):
+                pts.append((x0[g * m + i], x1[j]))
+    return np.array(pts)
+
+
+def macro_values(xy):
+    """Synthetic macro iterate (bounded, smooth): the shape of the exact macro solutions of linear.prm."""
+    u = xy[:, 1] * np.sin(xy[:, 0])
+    w = xy[:, 0] * np.cos(xy[:, 1])
+    return np.ascontiguousarray(u), np.ascontiguousarray(w)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                parts = [p.strip() for p in out.split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(float(parts[0]))
+                    self.max_mhz = float(parts[1])
+                    for nm, val in zip(names, parts[2:6]):
+                        if val.lower().startswith("active"):
+                            self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def algorithmic_bytes(n, nnz, iters, n_systems_total):
+    """SURVEY.md §8d byte model.  Returns (whole step, CG kernel only)."""
+    its = np.asarray(iters, dtype=np.float64)
+    step = (8.0 * nnz * (1.0 + its) + 24.0 * n + 4.0 * (nnz + n + 1) / max(1, n_systems_total)).sum()
+    cg = (8.0 * nnz * its + 24.0 * n).sum()
+    return float(step), float(cg)
+
+
+def cpu_baseline(prm_path, macro_cells, micro_cells, sample, threads):
+    """The CPU restatement (oracle) timed on a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import OracleBio  # test infrastructure: the checker / baseline, never the product
+
+    # a macro mesh just large enough to hold `sample` grids keeps the oracle's memory small
+    cells = 1
+    while (cells + 1) ** 2 < sample:
+        cells += 1
+    o = OracleBio(prm_path, cells, micro_cells, threads)
+    xy = o.grid_locations()
+    u, w = macro_values(xy)
+    sample = min(sample, o.N)
+    secs = o.time_micro(u, w, sample, threads)
+    its = o.iters()[:sample]
+    n = o.n
+    o.close()
+    return {"value": sample * n / secs, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample} of the {micro_cells}x{micro_cells}-cell micro systems (assemble + CG + flux integrals), "
+                      f"{threads} threads over systems, {secs:.2f} s; CPU restatement of the reference algorithm "
+                      f"(deal.II unavailable)",
+            "seconds": secs, "mean_cg_iterations": float(np.mean(its))}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    micro_cells = 2 ** args.micro_ref
+    prm_path = os.path.join(ROOT, "input", args.prm)
+    sample = args.cpu_sample or 128 * threads
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(prm_path, 2 ** args.macro_ref, micro_cells, max(1, sample // 2), threads)
+    t0 = time.time()
+    last = None
+    for _ in range(args.steps):
+        last = cpu_baseline(prm_path, 2 ** args.macro_ref, micro_cells, sample, threads)
+        vals.append(last["value"])
+    total = time.time() - t0
+    v = float(np.mean(vals))
+    last["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": last,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    mc, Mc = 2 ** args.micro_ref, 2 ** args.macro_ref
+    return {
+        "workload": f"solve_biomath {args.prm} {args.macro_ref} {args.micro_ref}: one fixed-point iteration of the micro "
+                    f"path (assemble + CG from zero start + flux integrals)",
+        "prm": args.prm, "micro_cells_per_axis": mc, "micro_dofs": (mc + 1) ** 2, "q_degree": 12,
+        "macro_points_per_gpu": (Mc + 1) ** 2, "macro_points_total": (Mc + 1) ** 2 * n_gpus,
+        "cg": "deal.II recurrence, identity preconditioner, abs tol 1e-12, max 10000",
+        "parallelism": f"macro points sharded over {n_gpus} GPU(s), allgather+broadcast per step" if n_gpus > 1
+                       else "single GPU",
+        "l2": "inputs larger than L2: 0.7 GB of matrix values + 1.9 GB of cell moments per step",
+    }
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the micro path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from dealiiscale_b200 import capi
+    from dealiiscale_b200.micro import MicroSolver, unique_id
+    from dealiiscale_b200.prm import BioData
+
+    n_gpus = world
+    micro_cells, macro_cells = 2 ** args.micro_ref, 2 ** args.macro_ref
+    prm_path = os.path.join(ROOT, "input", args.prm)
+    data = BioData(prm_path)
+    xy_all = macro_points(macro_cells, n_gpus)
+    n_total = xy_all.shape[0]
+    k0, k1 = capi.partition(n_total, n_gpus, rank)
+    u_all, w_all = macro_values(xy_all)
+
+    ms = MicroSolver(capi.BIO, data, micro_cells, device=local_rank)
+    # run on torch's current stream so that torch.cuda.Event brackets exactly the launching stream
+    ms.use_stream(torch.cuda.current_stream().cuda_stream)
+    ms.set_grid_locations(xy_all[k0:k1])
+    if distributed:
+        ids = [unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ms.attach_communicator(ids[0], rank, n_gpus, n_total)
+    ms.setup()
+    n = ms.n_dofs
+    m = micro_cells + 1
+    nnz = (3 * m - 2) ** 2
+
+    # pinned host staging for the end-to-end path
+    u_pin = torch.from_numpy(u_all.copy()).pin_memory()
+    w_pin = torch.from_numpy(w_all.copy()).pin_memory()
+    u_host, w_host = u_pin.numpy(), w_pin.numpy()
+
+    def step_device():
+        """inputs resident in HBM; results stay on the device"""
+        ms.zero_solutions()
+        ms.assemble_system()
+        its = ms.solve()
+        ms.coupling_on_device()
+        return its
+
+    def step_e2e():
+        """through the public API with host buffers: H2D of the macro iterate, D2H of the integrals"""
+        if distributed:
+            ms.broadcast_macro(u_host, w_host, root=0)
+        else:
+            ms.set_macro_solution(u_host[k0:k1], w_host[k0:k1])
+        ms.zero_solutions()
+        ms.assemble_system()
+        its = ms.solve()
+        cu, cw = ms.coupling()
+        return its, cu, cw
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ms.set_macro_solution(u_all[k0:k1], w_all[k0:k1])
+    for _ in range(max(3, args.warmup)):
+        its = step_device()
+    barrier()
+
+    # ---- timed region 1: device-resident -----------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms.enable_timing(True)
+    ms.stats(reset=True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        its = step_device()
+    ev1.record()
+    barrier()
+    t_dev = ev0.elapsed_time(ev1) * 1e-3
+    st = ms.stats(reset=True)
+    ms.enable_timing(False)
+
+    # ---- timed region 2: end to end through host buffers ----------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev2.record()
+    for _ in range(args.steps):
+        its_e, cu, cw = step_e2e()
+    ev3.record()
+    barrier()
+    t_e2e = max(ev2.elapsed_time(ev3) * 1e-3, 0.0)
+    t_e2e_wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # device-side durations (CUDA events on the launching stream, recorded inside libmsgpu)
+    dev_ms_step = (st["ms_tables"] + st["ms_moments"] + st["ms_gather"] + st["ms_cg"] + st["ms_coupling"]) / args.steps
+    times = torch.tensor([t_dev, t_e2e, dev_ms_step, st["ms_cg"] / args.steps], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e, dev_ms_step, cg_ms = [float(v) for v in times.tolist()]
+
+    step_bytes, cg_bytes = algorithmic_bytes(n, nnz, its, n_total)
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = json.load(open(peaks_path))["hbm_gbs"]
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("k_cg_resident_bytes_per_launch")
+        achieved = cg_bytes / (cg_ms * 1e-3) / 1e9
+        value = n_total * n * args.steps / t_dev
+        e2e_value = n_total * n * args.steps / t_e2e
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, n_gpus),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "wall_ms_per_step": 1e3 * t_e2e_wall / args.steps,
+                    "h2d_bytes_per_step": int(16 * (n_total if distributed else (k1 - k0))),
+                    "d2h_bytes_per_step": int(16 * n_total + 4 * (k1 - k0) + 16)},
+            "gpu_launches": int(st["launches"]),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm", "kernel": "k_cg_resident<512,9> (batched CG, one CTA per micro system)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": cg_bytes,
+                "note": "the CG keeps each system in shared memory: the matrix is read from HBM once per solve, "
+                        "not once per iteration, so algorithmic bytes / time can exceed the HBM peak (on-chip resident)",
+                "step_algorithmic_bytes": step_bytes,
+                "step_achieved_GBps": step_bytes / (dev_ms_step * 1e-3) / 1e9,
+                "frac_of_nominal_8TBps": achieved / 8000.0,
+            },
+            "phases_ms_per_step": {k: st[k] / args.steps for k in
+                                   ("ms_tables", "ms_moments", "ms_gather", "ms_cg", "ms_coupling")},
+            "cg_iterations": {"mean": float(its.mean()), "max": int(its.max()), "min": int(its.min())},
+        }
+        if not args.no_cpu_baseline and n_gpus == 1:
+            threads = os.cpu_count() or 1
+            line["cpu_baseline"] = cpu_baseline(prm_path, macro_cells, micro_cells, args.cpu_sample or 128 * threads,
+                                                threads)
+        print(json.dumps(line), flush=True)
+    ms.close()
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,190 @@
+// Multi-GPU exchange of the micro->macro coupling scalars and of the macro solution.
+//
+// No reference call site: in the reference the macro solver reads the micro solutions through
+// raw pointers (src/elliptic-elliptic/manager.cpp:25-26, src/tools/pde_data.h:76-90).  With the
+// macro DoFs sharded over ranks that hand-off becomes one allgather of N (bio: 2N) doubles and one
+// broadcast of the macro solution per fixed-point iteration.  Both are
+// latency-bound (<= 133 KB), so they are issued on the context's stream directly behind the
+// coupling kernel, which writes its results in place into this rank's block of the gather buffer.
+//
+// Partition: rank r owns the contiguous block [r*B, min((r+1)*B, n_total)) with B = ceil(n_total/R).
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is resolved at run time, see nccl_api()
+
+#include <cstring>
+
+#include "ctx.h"
+
+namespace msgpu {
+
+// NCCL is bound lazily with dlopen instead of at link time.  A host process that also uses
+// torch.distributed already carries torch's bundled libnccl.so.2; loading a second, older system
+// copy at library-load time would shadow it (and break `import torch` if libmsgpu came first).
+// RTLD_NOLOAD picks up whatever copy the process already has; only a stand-alone C++ host falls
+// back to the system library.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  const char* (*GetErrorString)(ncclResult_t);
+  bool ok = false;
+};
+
+static const NcclApi& nccl_api() {
+  static NcclApi api = [] {
+    NcclApi a{};
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return a;
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
+    a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(dlsym(h, "ncclBroadcast"));
+    a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(h, "ncclGroupStart"));
+    a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.Broadcast && a.GroupStart &&
+           a.GroupEnd && a.GetErrorString;
+    return a;
+  }();
+  return api;
+}
+
+static int nccl_fail(msgpu_ctx* ctx, ncclResult_t r, const char* what) {
+  ctx->err = std::string(what) + ": " + nccl_api().GetErrorString(r);
+  return MSGPU_ERR_COMM;
+}
+
+int comm_block(const msgpu_ctx* ctx) { return (ctx->n_total + ctx->n_ranks - 1) / ctx->n_ranks; }
+
+int comm_ensure_buffers(msgpu_ctx* ctx) {
+  const size_t padded = static_cast<size_t>(comm_block(ctx)) * ctx->n_ranks;
+  if (ctx->gather_capacity >= 2 * padded) return MSGPU_OK;
+  if (ctx->d_c) cudaFree(ctx->d_c);
+  if (ctx->d_macro) cudaFree(ctx->d_macro);
+  ctx->d_c = ctx->d_macro = nullptr;
+  if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_c), 2 * padded * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&ctx->d_macro), 2 * padded * sizeof(double)) != cudaSuccess) {
+    ctx->err = "cannot allocate the gather buffers";
+    return MSGPU_ERR_CUDA;
+  }
+  cudaMemsetAsync(ctx->d_c, 0, 2 * padded * sizeof(double), ctx->stream);
+  ctx->gather_capacity = 2 * padded;
+  return MSGPU_OK;
+}
+
+// In-place allgather of this rank's block(s) of d_c.  Layout: c0 at [0, padded), c1 at [padded, 2*padded).
+int comm_allgather_coupling(msgpu_ctx* ctx, double*, double*) {
+  ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm);
+  const int B = comm_block(ctx);
+  const size_t padded = static_cast<size_t>(B) * ctx->n_ranks;
+  const int fields = ctx->desc.problem == MSGPU_BIO ? 2 : 1;
+  const NcclApi& nc = nccl_api();
+  ncclResult_t r = nc.GroupStart();
+  if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclGroupStart");
+  for (int f = 0; f < fields; ++f) {
+    double* base = ctx->d_c + f * padded;
+    r = nc.AllGather(base + static_cast<size_t>(ctx->rank) * B, base, B, ncclDouble, comm, ctx->stream);
+    if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclAllGather");
+  }
+  r = nc.GroupEnd();
+  if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclGroupEnd");
+  ctx->launches += 1;
+  return MSGPU_OK;
+}
+
+void comm_destroy(msgpu_ctx* ctx) {
+  if (ctx->nccl_comm) {
+    nccl_api().CommDestroy(static_cast<ncclComm_t>(ctx->nccl_comm));
+    ctx->nccl_comm = nullptr;
+  }
+}
+
+}  // namespace msgpu
+
+using namespace msgpu;
+
+extern "C" {
+
+int msgpu_comm_unique_id(char id[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId u;
+  if (!nccl_api().ok || nccl_api().GetUniqueId(&u) != ncclSuccess) return MSGPU_ERR_COMM;
+  std::memcpy(id, &u, 128);
+  return MSGPU_OK;
+}
+
+int msgpu_partition(int n_total, int n_ranks, int rank, int* k0, int* k1) {
+  if (n_total < 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks || !k0 || !k1) return MSGPU_ERR_INVALID;
+  const int B = (n_total + n_ranks - 1) / n_ranks;
+  *k0 = rank * B < n_total ? rank * B : n_total;
+  *k1 = (rank + 1) * B < n_total ? (rank + 1) * B : n_total;
+  return MSGPU_OK;
+}
+
+int msgpu_comm_init(msgpu_ctx* ctx, const char id[128], int rank, int n_ranks, int n_total, int k_offset) {
+  if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return MSGPU_ERR_INVALID;
+  int k0, k1;
+  msgpu_partition(n_total, n_ranks, rank, &k0, &k1);
+  if (k_offset != k0 || (ctx->N != 0 && ctx->N != k1 - k0)) {
+    ctx->err = "rank block does not match msgpu_partition()";
+    return MSGPU_ERR_INVALID;
+  }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return MSGPU_ERR_CUDA;
+  ncclUniqueId u;
+  std::memcpy(&u, id, 128);
+  ncclComm_t comm;
+  if (!nccl_api().ok) {
+    ctx->err = "libnccl.so.2 cannot be loaded";
+    return MSGPU_ERR_COMM;
+  }
+  ncclResult_t r = nccl_api().CommInitRank(&comm, n_ranks, u, rank);
+  if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclCommInitRank");
+  ctx->nccl_comm = comm;
+  ctx->rank = rank;
+  ctx->n_ranks = n_ranks;
+  ctx->n_total = n_total;
+  ctx->k_offset = k_offset;
+  int rc = comm_ensure_buffers(ctx);
+  if (rc) return rc;
+  ctx->comm_ready = 1;
+  return MSGPU_OK;
+}
+
+// u_all / w_all: [n_total] host arrays; significant on root, overwritten on the other ranks.
+int msgpu_broadcast_macro(msgpu_ctx* ctx, double* u_all, double* w_all, int root) {
+  if (!ctx || !ctx->comm_ready || !ctx->setup_done || !u_all) return MSGPU_ERR_INVALID;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return MSGPU_ERR_CUDA;
+  ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm);
+  const size_t padded = static_cast<size_t>(comm_block(ctx)) * ctx->n_ranks;
+  const int fields = w_all ? 2 : 1;
+  double* host[2] = {u_all, w_all};
+  if (ctx->rank == root)
+    for (int f = 0; f < fields; ++f)
+      cudaMemcpyAsync(ctx->d_macro + f * padded, host[f], sizeof(double) * ctx->n_total, cudaMemcpyHostToDevice,
+                      ctx->stream);
+  ncclResult_t r = nccl_api().Broadcast(ctx->d_macro, ctx->d_macro, fields * padded, ncclDouble, root, comm, ctx->stream);
+  if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclBroadcast");
+  ctx->launches += 1;
+  cudaMemcpyAsync(ctx->d_u, ctx->d_macro + ctx->k_offset, sizeof(double) * ctx->N, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (w_all)
+    cudaMemcpyAsync(ctx->d_w, ctx->d_macro + padded + ctx->k_offset, sizeof(double) * ctx->N, cudaMemcpyDeviceToDevice,
+                    ctx->stream);
+  if (ctx->rank != root)
+    for (int f = 0; f < fields; ++f)
+      cudaMemcpyAsync(host[f], ctx->d_macro + f * padded, sizeof(double) * ctx->n_total, cudaMemcpyDeviceToHost,
+                      ctx->stream);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    ctx->err = "broadcast failed";
+    return MSGPU_ERR_CUDA;
+  }
+  return MSGPU_OK;
+}
+
+}  // extern "C"

@@ -75,5 +75,6 @@ struct msgpu_ctx {
   // multi-GPU
   int comm_ready = 0, rank = 0, n_ranks = 1, n_total = 0, k_offset = 0;
   void* nccl_comm = nullptr;
+  size_t gather_capacity = 0;  // doubles available in d_c / d_macro
   std::vector<int> rank_counts, rank_offsets;
 };

@@ -139,6 +139,7 @@ int parabolic_assemble(msgpu_ctx* ctx, double dt, double t);
 int compute_errors(msgpu_ctx* ctx, double* l2, double* h1);
 int compute_residuals(msgpu_ctx* ctx, double* l2);
 int comm_allgather_coupling(msgpu_ctx* ctx, double* c0, double* c1);
+int comm_block(const msgpu_ctx* ctx);
 void comm_destroy(msgpu_ctx* ctx);
 }  // namespace msgpu
 
@@ -344,7 +345,10 @@ int msgpu_setup(msgpu_ctx* ctx) {
   if ((rc = dev_alloc(ctx, &ctx->d_x, N * n))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_u, static_cast<size_t>(N)))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_w, static_cast<size_t>(N)))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->d_c, 2 * static_cast<size_t>(std::max(N, ctx->n_total))))) return rc;
+  if (!ctx->comm_ready) {
+    if ((rc = dev_alloc(ctx, &ctx->d_c, 2 * static_cast<size_t>(N)))) return rc;
+    ctx->gather_capacity = 2 * static_cast<size_t>(N);
+  }
   if ((rc = dev_alloc(ctx, &ctx->d_res, static_cast<size_t>(N)))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_iters, static_cast<size_t>(N)))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_flags, static_cast<size_t>(4)))) return rc;
@@ -517,12 +521,14 @@ int msgpu_time_step(msgpu_ctx* ctx, double dt, double t, double abs_tol, int max
 }
 
 int msgpu_coupling(msgpu_ctx* ctx, double* c0, double* c1) {
-  if (!ctx || !ctx->setup_done || !c0) return MSGPU_ERR_INVALID;
+  if (!ctx || !ctx->setup_done) return MSGPU_ERR_INVALID;
   const int prob = ctx->desc.problem;
-  if (prob == MSGPU_BIO && !c1) return fail(ctx, MSGPU_ERR_INVALID, "bio coupling needs both output arrays");
+  if (prob == MSGPU_BIO && c0 && !c1) return fail(ctx, MSGPU_ERR_INVALID, "bio coupling needs both output arrays");
   CK(cudaSetDevice(ctx->device));
   const int ntot = ctx->comm_ready ? ctx->n_total : ctx->N;
   const int koff = ctx->comm_ready ? ctx->k_offset : 0;
+  // second field (bio outflow integrals) starts after the padded first field
+  const size_t field = ctx->comm_ready ? static_cast<size_t>(comm_block(ctx)) * ctx->n_ranks : static_cast<size_t>(ctx->N);
   {
     PhaseTimer pt(ctx, PH_COUPLING);
     CouplingArgs a;
@@ -536,7 +542,7 @@ int msgpu_coupling(msgpu_ctx* ctx, double* c0, double* c1) {
     a.kappa_left = prob == MSGPU_BIO ? ctx->scalars[1] : 0.0;
     a.kappa_right = prob == MSGPU_BIO ? ctx->scalars[3] : 0.0;
     a.c0 = ctx->d_c + koff;          // written straight into this rank's block of the gather buffer
-    a.c1 = ctx->d_c + ntot + koff;
+    a.c1 = ctx->d_c + field + koff;
     ctx->launches += launch_coupling(ctx->stream, a);
     CK(cudaGetLastError());
     if (ctx->comm_ready) {
@@ -544,9 +550,10 @@ int msgpu_coupling(msgpu_ctx* ctx, double* c0, double* c1) {
       if (rc) return rc;
     }
   }
+  if (!c0) return MSGPU_OK;
   CK(cudaMemcpyAsync(c0, ctx->d_c, sizeof(double) * ntot, cudaMemcpyDeviceToHost, ctx->stream));
   if (c1 && prob == MSGPU_BIO)
-    CK(cudaMemcpyAsync(c1, ctx->d_c + ntot, sizeof(double) * ntot, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(c1, ctx->d_c + field, sizeof(double) * ntot, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return MSGPU_OK;
 }
@@ -586,6 +593,12 @@ int msgpu_set_solutions(msgpu_ctx* ctx, int k0, int k1, const double* in) {
     for (size_t i = 0; i < n; ++i) tmp[k * n + ctx->ref_to_internal[i]] = in[k * n + i];
   CK(cudaMemcpyAsync(ctx->d_x + k0 * n, tmp.data(), sizeof(double) * tmp.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return MSGPU_OK;
+}
+
+int msgpu_zero_solutions(msgpu_ctx* ctx) {
+  if (!ctx || !ctx->setup_done) return MSGPU_ERR_INVALID;
+  CK(cudaMemsetAsync(ctx->d_x, 0, sizeof(double) * ctx->N * ctx->md.n, ctx->stream));
   return MSGPU_OK;
 }
 

@@ -130,7 +130,8 @@ int msgpu_time_step(msgpu_ctx* ctx, double dt, double t, double abs_tol, int max
  * elliptic  c0[k] = int v_k J dy                      (macro.cpp:134-166)
  * bio       c0[k], c1[k] = inflow / outflow integrals (bio macro.cpp:254-306)
  * parabolic c0[k] = int rho_k dy                      (pi_solver.cpp:178-197)
- * With a communicator (msgpu_comm_init) the arrays have n_total entries and are allgathered. */
+ * With a communicator (msgpu_comm_init) the arrays have n_total entries and are allgathered.
+ * c0 == NULL: compute (and allgather) on the device only, no copy to the host. */
 int msgpu_coupling(msgpu_ctx* ctx, double* c0, double* c1);
 
 /* ---- next tier: MicroSolver::compute_all_errors per-grid part (micro.cpp:189-205),
@@ -142,6 +143,8 @@ int msgpu_residuals(msgpu_ctx* ctx, double* l2);
 /* ---- public data of MicroSolver: solutions (micro.h:97), in reference DoF numbering -------- */
 int msgpu_get_solutions(msgpu_ctx* ctx, int k0, int k1, double* out /* [k1-k0][n] */);
 int msgpu_set_solutions(msgpu_ctx* ctx, int k0, int k1, const double* in);
+/* solutions.at(k) = 0 for all k (micro.cpp:151), on the device. */
+int msgpu_zero_solutions(msgpu_ctx* ctx);
 int msgpu_get_rhs(msgpu_ctx* ctx, int k0, int k1, double* out /* [k1-k0][n] */);
 /* ref_to_internal[n]: position of reference DoF i in the device ordering. */
 int msgpu_get_dof_permutation(msgpu_ctx* ctx, int* ref_to_internal);
@@ -154,6 +157,8 @@ int msgpu_get_matrix_dense(msgpu_ctx* ctx, int k, double* out /* [n][n] */);
  * (no reference call site: replaces the pointer hand-off of manager.cpp:25-26).
  * id: 128 bytes from msgpu_comm_unique_id on rank 0, distributed by the caller. */
 int msgpu_comm_unique_id(char id[128]);
+/* The partition every rank must use: rank r owns [k0,k1) = [r*B, min((r+1)*B, n_total)), B = ceil(n_total/n_ranks). */
+int msgpu_partition(int n_total, int n_ranks, int rank, int* k0, int* k1);
 int msgpu_comm_init(msgpu_ctx* ctx, const char id[128], int rank, int n_ranks, int n_total, int k_offset);
 /* Broadcast of the macro solution from root; every rank keeps its own block (set_macro_solution). */
 int msgpu_broadcast_macro(msgpu_ctx* ctx, double* u_all, double* w_all, int root);

@@ -9,6 +9,7 @@
 
 #include "bio.h"
 #include "elliptic.h"
+#include "mapmap.h"
 #include "parabolic.h"
 
 using namespace orc;
@@ -77,6 +78,31 @@ int orc_numbering(int kind, int nc, int* node_dof) {
   });
 }
 
+// ---- MapMap (reference tests/test_tools.cpp:45-103) ---------------------------------------------
+void* orc_mapmap_create() { return new MapMap(); }
+void orc_mapmap_destroy(void* h) { delete static_cast<MapMap*>(h); }
+void orc_mapmap_set(void* h, const double* px, int nx, const double* py, int ny, double det, const double* kkt3) {
+  static_cast<MapMap*>(h)->set(std::vector<double>(px, px + nx), std::vector<double>(py, py + ny), det,
+                               {kkt3[0], kkt3[1], kkt3[2]});
+}
+int orc_mapmap_get(void* h, const double* px, int nx, const double* py, int ny, double* det, double* kkt3) {
+  return guarded([&] {
+    std::array<double, 3> k;
+    static_cast<MapMap*>(h)->get(std::vector<double>(px, px + nx), std::vector<double>(py, py + ny), *det, k);
+    kkt3[0] = k[0];
+    kkt3[1] = k[1];
+    kkt3[2] = k[2];
+    return 0;
+  });
+}
+int orc_mapmap_size(void* h) { return static_cast<int>(static_cast<MapMap*>(h)->size()); }
+int orc_mapmap_key(const double* px, int nx, const double* py, int ny, char* buf, int len) {
+  std::string k = MapMap::to_string(std::vector<double>(px, px + nx), std::vector<double>(py, py + ny));
+  std::strncpy(buf, k.c_str(), len - 1);
+  buf[len - 1] = 0;
+  return static_cast<int>(k.size());
+}
+
 // ---- elliptic-elliptic ---------------------------------------------------------------------
 void* orc_ell_create(const char* prm, int macro_ref, int micro_ref) {
   try {
@@ -129,6 +155,13 @@ void orc_ell_get_solution(void* h, int k, double* out) {
 void orc_ell_get_iters(void* h, int* out) {
   auto& v = static_cast<elliptic::Manager*>(h)->micro_solver.cg_iterations;
   std::copy(v.begin(), v.end(), out);
+}
+// recursive residuals of the last solve of grid k (entry i = after i steps); returns the count
+int orc_ell_cg_history(void* h, int k, double* out, int maxlen) {
+  auto& v = static_cast<elliptic::Manager*>(h)->micro_solver.cg_history[k];
+  int n = std::min<int>(maxlen, static_cast<int>(v.size()));
+  std::copy(v.begin(), v.begin() + n, out);
+  return static_cast<int>(v.size());
 }
 void orc_ell_bulk(void* h, double* c) {
   auto* m = static_cast<elliptic::Manager*>(h);

@@ -202,6 +202,7 @@ struct MicroSolver {
   std::vector<double> det_jac, kkt;
   std::vector<double> qx, qw;
   std::vector<int> cg_iterations;
+  std::vector<std::vector<double>> cg_history;  // oracle extension: recursive residual per step
 
   MicroSolver(MultiscaleData& d, int refine) : data(d), refine_level(refine) {}
 
@@ -222,6 +223,7 @@ struct MicroSolver {
     righthandsides.assign(num_grids, std::vector<double>(n, 0.0));
     system_matrices.assign(num_grids, SparseMatrix());
     cg_iterations.assign(num_grids, 0);
+    cg_history.assign(num_grids, {});
     gauss01(fem_q_deg, qx, qw);
     compute_pullback_objects();
   }
@@ -321,7 +323,7 @@ struct MicroSolver {
     for (int k = 0; k < num_grids; ++k) solve_one(k);
   }
   void solve_one(int k) {
-    CGResult r = solve_cg(system_matrices[k], solutions[k], righthandsides[k], 1000, 1e-12);
+    CGResult r = solve_cg(system_matrices[k], solutions[k], righthandsides[k], 1000, 1e-12, &cg_history[k]);
     if (!r.converged) throw std::runtime_error("micro CG: SolverControl::NoConvergence");
     cg_iterations[k] = r.iterations;
   }

@@ -256,7 +256,7 @@ struct CGResult {
 // SolverControl(max_steps, tol): recursive residual, absolute tolerance.
 // Called at reference micro.cpp:176-179, bio micro.cpp:310-313, rho_solver.cpp:223-226.
 inline CGResult solve_cg(const SparseMatrix& A, std::vector<double>& x, const std::vector<double>& b,
-                         int max_steps, double tol) {
+                         int max_steps, double tol, std::vector<double>* history = nullptr) {
   const int n = A.sp->n;
   std::vector<double> g(n), d(n), h(n);
   bool all_zero = true;
@@ -279,6 +279,10 @@ inline CGResult solve_cg(const SparseMatrix& A, std::vector<double>& x, const st
   CGResult r;
   double res = std::sqrt(dot(g, g));
   r.residual = res;
+  if (history) {
+    history->clear();
+    history->push_back(res);
+  }
   if (res <= tol) {
     r.converged = true;
     return r;
@@ -297,6 +301,7 @@ inline CGResult solve_cg(const SparseMatrix& A, std::vector<double>& x, const st
     res = std::sqrt(dot(g, g));
     r.iterations = it;
     r.residual = res;
+    if (history) history->push_back(res);
     if (res <= tol) {
       r.converged = true;
       return r;

@@ -236,6 +236,11 @@ class OracleElliptic:
         self.lib.orc_ell_get_iters(self.h, iptr(out))
         return out
 
+    def cg_history(self, k):
+        buf = np.zeros(20001)
+        n = self.lib.orc_ell_cg_history(self.h, k, dptr(buf), len(buf))
+        return buf[:n]
+
     def bulk(self):
         out = np.zeros(self.N)
         self.lib.orc_ell_bulk(self.h, dptr(out))
@@ -277,3 +282,126 @@ def rel_l2(a, b):
     a, b = np.asarray(a), np.asarray(b)
     nb = np.linalg.norm(b)
     return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
+
+
+class OracleBio:
+    def __init__(self, prm, macro_cells, micro_cells, threads=4):
+        self.lib = load_oracle()
+        self.lib.orc_bio_create.restype = C.c_void_p
+        self.lib.orc_bio_time_micro.restype = C.c_double
+        path = prm if os.path.isabs(prm) else os.path.join(INPUT, prm)
+        h = self.lib.orc_bio_create(path.encode(), macro_cells, micro_cells, threads)
+        if not h:
+            raise RuntimeError(self.lib.orc_last_error().decode())
+        self.h = C.c_void_p(h)
+        N, n = C.c_int(), C.c_int()
+        self.lib.orc_bio_sizes(self.h, C.byref(N), C.byref(n))
+        self.N, self.n = N.value, n.value
+
+    def close(self):
+        if self.h:
+            self.lib.orc_bio_destroy(self.h)
+            self.h = None
+
+    def has_solution(self):
+        return bool(self.lib.orc_bio_has_solution(self.h))
+
+    def grid_locations(self):
+        xy = np.zeros((self.N, 2))
+        self.lib.orc_bio_grid_locations(self.h, dptr(xy))
+        return xy
+
+    def dof_points(self):
+        xy = np.zeros((self.n, 2))
+        self.lib.orc_bio_dof_points(self.h, dptr(xy))
+        return xy
+
+    def micro_run(self, u, w, assemble_only=False):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        if self.lib.orc_bio_micro_run(self.h, dptr(u), dptr(w), int(assemble_only)) != 0:
+            raise RuntimeError(self.lib.orc_last_error().decode())
+
+    def set_solution(self, k, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self.lib.orc_bio_set_solution(self.h, k, dptr(x))
+
+    def matrix(self, k):
+        out = np.zeros((self.n, self.n))
+        self.lib.orc_bio_get_matrix_dense(self.h, k, dptr(out))
+        return out
+
+    def rhs(self, k):
+        out = np.zeros(self.n)
+        self.lib.orc_bio_get_rhs(self.h, k, dptr(out))
+        return out
+
+    def solution(self, k):
+        out = np.zeros(self.n)
+        self.lib.orc_bio_get_solution(self.h, k, dptr(out))
+        return out
+
+    def iters(self):
+        out = np.zeros(self.N, dtype=np.int32)
+        self.lib.orc_bio_get_iters(self.h, iptr(out))
+        return out
+
+    def cg_history(self, k):
+        buf = np.zeros(20001)
+        n = self.lib.orc_bio_cg_history(self.h, k, dptr(buf), len(buf))
+        return buf[:n]
+
+    def flux(self):
+        cu, cw = np.zeros(self.N), np.zeros(self.N)
+        self.lib.orc_bio_flux(self.h, dptr(cu), dptr(cw))
+        return cu, cw
+
+    def grid_errors(self):
+        l2, h1 = np.zeros(self.N), np.zeros(self.N)
+        self.lib.orc_bio_grid_errors(self.h, dptr(l2), dptr(h1))
+        return l2, h1
+
+    def grid_residuals(self):
+        l2 = np.zeros(self.N)
+        self.lib.orc_bio_grid_residuals(self.h, dptr(l2))
+        return l2
+
+    def run(self, cycle_limit=-1):
+        r = self.lib.orc_bio_run(self.h, cycle_limit)
+        if r < 0:
+            raise RuntimeError(self.lib.orc_last_error().decode())
+        return r
+
+    def history(self, cycle, solutions=True):
+        sc = np.zeros(6)
+        su, sw, cu, cw = (np.zeros(self.N) for _ in range(4))
+        micro = np.zeros((self.N, self.n)) if solutions else None
+        its = np.zeros(self.N, dtype=np.int32)
+        self.lib.orc_bio_history(self.h, cycle, dptr(sc), dptr(su) if solutions else None,
+                                 dptr(sw) if solutions else None, dptr(cu), dptr(cw),
+                                 dptr(micro) if solutions else None, iptr(its))
+        return dict(micro_l2=sc[0], micro_h1=sc[1], macro_l2=sc[2], macro_h1=sc[3], macro_residual=sc[4],
+                    micro_residual=sc[5], sol_u=su, sol_w=sw, cu=cu, cw=cw, micro=micro, micro_iters=its)
+
+    def time_micro(self, u, w, n_sys, threads):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        return self.lib.orc_bio_time_micro(self.h, dptr(u), dptr(w), n_sys, threads)
+
+
+def assert_iterations_consistent(oracle, its_gpu, tol=1e-12, window=3, graze=10.0):
+    """CG iteration counts must equal the oracle's, except where the oracle's own recursive residual
+    is already within a factor `graze` of the stopping threshold at the earlier of the two counts:
+    there the last few steps are driven by rounding (different summation orders in the dot products)
+    and the count may differ by up to `window` steps.  Returns the number of such systems."""
+    its_o = oracle.iters()
+    grazing = 0
+    for k, (a, b) in enumerate(zip(its_gpu, its_o)):
+        if a == b:
+            continue
+        lo, hi = min(a, b), max(a, b)
+        assert hi - lo <= window, f"grid {k}: {a} vs {b} CG steps"
+        hist = oracle.cg_history(k)
+        assert hist[lo] <= graze * tol, f"grid {k}: {a} vs {b} CG steps, oracle residual at step {lo} is {hist[lo]:.2e}"
+        grazing += 1
+    return grazing
