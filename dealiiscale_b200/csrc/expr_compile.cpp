@@ -566,7 +566,8 @@ void ProgramSet::finalize() {
 
   // 4. table-building programs
   auto build_table_program = [&](Cls c, const std::vector<int>& order, VmProgram& prog) {
-    CodeGen g(*this, c, MODE_LINES, prog, VM_REG_OUT0);
+    CodeGen g(*this, c, MODE_LINES, prog, VM_REG_TMP0);
+    prog.out0 = 0;
     for (int id : order) g.count_uses(id);
     for (size_t i = 0; i < order.size(); ++i) {
       g.emit_store(order[i], VK_OUT, static_cast<int>(i));
@@ -582,9 +583,12 @@ void ProgramSet::finalize() {
   point_progs_.assign(specs_.size(), VmProgram{});
   for (size_t s = 0; s < specs_.size(); ++s) {
     const Spec& sp = specs_[s];
-    CodeGen g(*this, CLS_POINT, sp.mode, point_progs_[s], VM_REG_OUT0 + static_cast<int>(sp.outputs.size()));
+    // MODE_LINES programs have no register inputs; MODE_POINTS programs read y0, y1 from R[0], R[1]
+    const int out0 = sp.mode == MODE_LINES ? 0 : 2;
+    point_progs_[s].out0 = out0;
+    CodeGen g(*this, CLS_POINT, sp.mode, point_progs_[s], out0 + static_cast<int>(sp.outputs.size()));
     for (int o : sp.outputs) g.count_uses(o);
-    for (size_t i = 0; i < sp.outputs.size(); ++i) g.emit_store(sp.outputs[i], VK_REG, VM_REG_OUT0 + static_cast<int>(i));
+    for (size_t i = 0; i < sp.outputs.size(); ++i) g.emit_store(sp.outputs[i], VK_REG, out0 + static_cast<int>(i));
     g.finish();
   }
   finalized_ = true;

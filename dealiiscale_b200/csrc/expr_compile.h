@@ -63,7 +63,7 @@ class ProgramSet {
   std::vector<int> parse_function(const std::string& text, const std::map<std::string, double>& constants,
                                   bool time_dependent, int n_components, int mapped_y0 = -1, int mapped_y1 = -1);
 
-  // A point program evaluates `outputs` (node ids) into registers VM_REG_OUT0.. in order.
+  // A point program evaluates `outputs` (node ids) into registers prog.out0, prog.out0+1, .. in order.
   int add_point_program(const std::vector<int>& outputs, EvalMode mode);
 
   // Decides what is materialised where and generates all programs.

@@ -45,9 +45,20 @@ int launch_lines(cudaStream_t s, const VmProgram& prog0, const VmProgram& prog1,
                  int n1);
 
 // K1 cell moments: for systems [k0, k0+nk) writes cell[(kl*CELL_STRIDE + e)*ncells + c].
-// Program outputs: F00 F01 F10 F11 G  (has_map) or just G (no mapping: F = identity).
-int launch_cell_moments(cudaStream_t s, const VmProgram& prog, MeshDims md, Tables tb, const double* qtab, int k0, int nk,
-                        double stiffness_scale, int has_map, double* cell, int* error_flag);
+// full: F00 F01 F10 F11 G per quadrature point; F / G: the two halves as separate programs.
+// When F does not depend on y (or there is no mapping) the stiffness part is closed-form and only
+// G is evaluated per quadrature point.
+struct MomentPrograms {
+  const VmProgram* full;
+  const VmProgram* F;
+  const VmProgram* G;
+  int has_map;
+  int jac_depends_on_y;
+};
+int launch_cell_moments(cudaStream_t s, const MomentPrograms& mp, MeshDims md, Tables tb, const double* qtab,
+                        const double* qsum, int k0, int nk, double stiffness_scale, double* cell, int* error_flag);
+// one-time upload of the per-quadrature-point tables into constant memory (q = 2, 3, 12)
+int upload_constant_tables(int q, const double* qtab, const double* qsum);
 
 // K1 faces: for systems [k0,k0+nk) and side in {0:x=-1, 1:x=+1, 2:y=-1, 3:y=+1} writes
 // face[((kl*4 + side)*FACE_STRIDE + e)*nc + f].  One program per side: outputs F00..F11, BC.

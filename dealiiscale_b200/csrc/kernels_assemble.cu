@@ -10,6 +10,7 @@
 // the coalesced write of 18 doubles per cell and the read of the line tables, which are
 // warp-uniform (y0 side) or unit-stride (y1 side) by construction of the device ordering.
 #include <cstdio>
+#include <cstdlib>
 
 #include "assemble_bodies.cuh"
 #include "kernels.h"
@@ -23,6 +24,72 @@ constexpr int TB = 128;  // threads per block of the assembly kernels
 inline size_t vm_smem(const VmProgram& p, int threads) {
   int regs = p.n_regs < 8 ? 8 : p.n_regs;
   return static_cast<size_t>(regs) * threads * sizeof(double);
+}
+
+inline int blocks_for(long long work) { return static_cast<int>((work + TB - 1) / TB); }
+
+// Per-quadrature-point basis products in constant memory: every lane of a warp reads the same
+// entry, so these become uniform constant-bank operands.  The contents depend on q only.
+__constant__ double c_qtab12[144 * QTAB_STRIDE];
+__constant__ double c_qsum12[QTAB_STRIDE];
+__constant__ double c_qtab3[9 * QTAB_STRIDE];
+__constant__ double c_qsum3[QTAB_STRIDE];
+__constant__ double c_qtab2[4 * QTAB_STRIDE];
+__constant__ double c_qsum2[QTAB_STRIDE];
+
+template <int Q>
+struct TabConst;
+#ifdef __CUDA_ARCH__
+#define MSGPU_CONST_TAB(Q, TAB, SUM)                                                        \
+  template <>                                                                               \
+  struct TabConst<Q> {                                                                      \
+    __host__ __device__ double operator()(int q, int i) const { return TAB[q * QTAB_STRIDE + i]; } \
+    __host__ __device__ double total(int i) const { return SUM[i]; }                        \
+  };
+#else
+#define MSGPU_CONST_TAB(Q, TAB, SUM)                                                        \
+  template <>                                                                               \
+  struct TabConst<Q> {                                                                      \
+    __host__ __device__ double operator()(int, int) const { return 0.0; }                   \
+    __host__ __device__ double total(int) const { return 0.0; }                             \
+  };
+#endif
+MSGPU_CONST_TAB(12, c_qtab12, c_qsum12)
+MSGPU_CONST_TAB(3, c_qtab3, c_qsum3)
+MSGPU_CONST_TAB(2, c_qtab2, c_qsum2)
+
+template <int Q, int W, int MODE>
+__global__ void __launch_bounds__(TB) k_cell_moments_vec(const __grid_constant__ VmProgram progF,
+                                                          const __grid_constant__ VmProgram prog, MeshDims md, Tables tb,
+                                                          int k0, int nk, double stiffness_scale,
+                                                          double* __restrict__ cell, int* __restrict__ error_flag) {
+  extern __shared__ double R[];
+  body_cell_moments_vec<Q, W, MODE>(progF, prog, md, tb, TabConst<Q>(), k0, nk, stiffness_scale, cell, error_flag,
+                                    static_cast<long long>(blockIdx.x) * TB + threadIdx.x, R + threadIdx.x, TB);
+}
+
+template <int Q, int W, int MODE>
+int launch_moments_vec(cudaStream_t s, const VmProgram& progF, const VmProgram& prog, MeshDims md, Tables tb, int k0,
+                       int nk, double scale, double* cell, int* error_flag) {
+  size_t regs = static_cast<size_t>(prog.n_regs) * W;
+  if (MODE == MODE_CONST_F && static_cast<size_t>(progF.n_regs) > regs) regs = progF.n_regs;
+  if (regs < 8) regs = 8;
+  const size_t smem = regs * TB * sizeof(double);
+  if (smem > 200 * 1024) return -1;
+  auto kern = k_cell_moments_vec<Q, W, MODE>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  kern<<<blocks_for(static_cast<long long>(nk) * md.ncells), TB, smem, s>>>(progF, prog, md, tb, k0, nk, scale, cell,
+                                                                            error_flag);
+  return 1;
+}
+
+template <int Q, int WG, int WC>
+int dispatch_moments(cudaStream_t s, const MomentPrograms& mp, MeshDims md, Tables tb, int k0, int nk, double scale,
+                     double* cell, int* error_flag) {
+  if (!mp.has_map) return launch_moments_vec<Q, WC, MODE_NO_MAP>(s, *mp.G, *mp.G, md, tb, k0, nk, scale, cell, error_flag);
+  if (!mp.jac_depends_on_y)
+    return launch_moments_vec<Q, WC, MODE_CONST_F>(s, *mp.F, *mp.G, md, tb, k0, nk, scale, cell, error_flag);
+  return launch_moments_vec<Q, WG, MODE_GENERAL>(s, *mp.full, *mp.full, md, tb, k0, nk, scale, cell, error_flag);
 }
 
 // Thin __global__ wrappers: thread id -> body.  TB threads per block, one VM register file of
@@ -73,8 +140,6 @@ __global__ void __launch_bounds__(TB) k_mask_dirichlet(MeshDims md, int N, doubl
   body_mask_dirichlet(md, N, diag, static_cast<long long>(blockIdx.x) * TB + threadIdx.x);
 }
 
-inline int blocks_for(long long work) { return static_cast<int>((work + TB - 1) / TB); }
-
 }  // namespace
 
 int launch_slots(cudaStream_t s, const VmProgram& prog, const double* xy, int N, double t, double* slots, int n_slots) {
@@ -95,12 +160,39 @@ int launch_lines(cudaStream_t s, const VmProgram& prog0, const VmProgram& prog1,
   return 1;
 }
 
-int launch_cell_moments(cudaStream_t s, const VmProgram& prog, MeshDims md, Tables tb, const double* qtab, int k0,
-                        int nk, double stiffness_scale, int has_map, double* cell, int* error_flag) {
+int launch_cell_moments(cudaStream_t s, const MomentPrograms& mp, MeshDims md, Tables tb, const double* qtab,
+                        const double* qsum, int k0, int nk, double stiffness_scale, double* cell, int* error_flag) {
   if (nk == 0) return 0;
+  const bool scalar_only = std::getenv("MSGPU_SCALAR_VM") != nullptr;  // A/B switch for measurements
+  int r = -1;
+  if (!scalar_only) {
+    if (md.q == 12) r = dispatch_moments<12, 6, 12>(s, mp, md, tb, k0, nk, stiffness_scale, cell, error_flag);
+    else if (md.q == 3) r = dispatch_moments<3, 3, 3>(s, mp, md, tb, k0, nk, stiffness_scale, cell, error_flag);
+    else if (md.q == 2) r = dispatch_moments<2, 2, 2>(s, mp, md, tb, k0, nk, stiffness_scale, cell, error_flag);
+  }
+  if (r >= 0) return r;
+  // generic quadrature degree (or a program with very many temporaries): one VM run per point
+  const VmProgram& prog = mp.has_map ? *mp.full : *mp.G;
+  (void)qsum;
   k_cell_moments<<<blocks_for(static_cast<long long>(nk) * md.ncells), TB, vm_smem(prog, TB), s>>>(
-      prog, md, tb, qtab, k0, nk, stiffness_scale, has_map, cell, error_flag);
+      prog, md, tb, qtab, k0, nk, stiffness_scale, mp.has_map, cell, error_flag);
   return 1;
+}
+
+int upload_constant_tables(int q, const double* qtab, const double* qsum) {
+  cudaError_t e = cudaSuccess;
+  const size_t bytes = static_cast<size_t>(q) * q * QTAB_STRIDE * sizeof(double), sb = QTAB_STRIDE * sizeof(double);
+  if (q == 12) {
+    e = cudaMemcpyToSymbol(c_qtab12, qtab, bytes);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_qsum12, qsum, sb);
+  } else if (q == 3) {
+    e = cudaMemcpyToSymbol(c_qtab3, qtab, bytes);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_qsum3, qsum, sb);
+  } else if (q == 2) {
+    e = cudaMemcpyToSymbol(c_qtab2, qtab, bytes);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_qsum2, qsum, sb);
+  }
+  return e == cudaSuccess ? 0 : 1;
 }
 
 int launch_face_moments(cudaStream_t s, const VmProgram& prog, int side, MeshDims md, Tables tb, const double* q1d_pt,

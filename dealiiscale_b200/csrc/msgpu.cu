@@ -300,6 +300,11 @@ int msgpu_setup(msgpu_ctx* ctx) {
   ctx->q_pt = pt;
   ctx->q_wt = wt;
   std::vector<double> qtab = build_qtab(md.q, pt, wt);
+  std::vector<double> qsum(QTAB_STRIDE, 0.0);
+  for (int q = 0; q < md.q * md.q; ++q)
+    for (int i = 0; i < QTAB_STRIDE; ++i) qsum[i] += qtab[static_cast<size_t>(q) * QTAB_STRIDE + i];
+  if (upload_constant_tables(md.q, qtab.data(), qsum.data()))
+    return fail(ctx, MSGPU_ERR_CUDA, "cannot upload the quadrature tables to constant memory");
   std::vector<double> c0(md.P), c1(md.P);
   for (int p = 0; p < md.nc * md.q; ++p) {
     const int cx = p / md.q, qx = p % md.q;
@@ -317,7 +322,7 @@ int msgpu_setup(msgpu_ctx* ctx) {
   if ((rc = dev_alloc(ctx, &ctx->d_T1, static_cast<size_t>(N) * std::max(1, ps.n_line1()) * md.P))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_coord0, static_cast<size_t>(md.P)))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_coord1, static_cast<size_t>(md.P)))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->d_qtab, qtab.size()))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_qtab, qtab.size() + QTAB_STRIDE))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_q1pt, static_cast<size_t>(md.q)))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_q1wt, static_cast<size_t>(md.q)))) return rc;
   // chunk of systems whose cell / face moments are in flight at once (<= 2 GiB of scratch)
@@ -358,6 +363,8 @@ int msgpu_setup(msgpu_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->d_coord0, c0.data(), sizeof(double) * md.P, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_coord1, c1.data(), sizeof(double) * md.P, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_qtab, qtab.data(), sizeof(double) * qtab.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_qtab + qtab.size(), qsum.data(), sizeof(double) * QTAB_STRIDE, cudaMemcpyHostToDevice,
+                     ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_q1pt, pt.data(), sizeof(double) * md.q, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_q1wt, wt.data(), sizeof(double) * md.q, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_x, 0, N * n * sizeof(double), ctx->stream));
@@ -405,8 +412,15 @@ int msgpu_assemble(msgpu_ctx* ctx) {
     const int nk = std::min(ctx->chunk, ctx->N - k0);
     {
       PhaseTimer pt(ctx, PH_MOMENTS);
-      ctx->launches += launch_cell_moments(ctx->stream, ps.point_program(ctx->pp.prog_vol), md, tb, ctx->d_qtab, k0, nk,
-                                           d2, ctx->pp.has_map, ctx->d_cell, ctx->d_flags + FLAG_JACOBIAN);
+      MomentPrograms mp;
+      mp.full = &ps.point_program(ctx->pp.prog_vol);
+      mp.F = ctx->pp.prog_vol_F >= 0 ? &ps.point_program(ctx->pp.prog_vol_F) : mp.full;
+      mp.G = &ps.point_program(ctx->pp.prog_vol_G);
+      mp.has_map = ctx->pp.has_map;
+      mp.jac_depends_on_y = ctx->pp.jac_depends_on_y;
+      ctx->launches += launch_cell_moments(ctx->stream, mp, md, tb, ctx->d_qtab,
+                                           ctx->d_qtab + static_cast<size_t>(md.q) * md.q * QTAB_STRIDE, k0, nk, d2,
+                                           ctx->d_cell, ctx->d_flags + FLAG_JACOBIAN);
       if (prob == MSGPU_BIO)
         for (int s = 0; s < 4; ++s)
           ctx->launches += launch_face_moments(ctx->stream, ps.point_program(ctx->pp.prog_face[s]), s, md, tb, ctx->d_q1pt,

@@ -36,8 +36,11 @@ int build_problem_programs(int problem, const FnDef* fn, ProblemPrograms& out, s
         return ps.parse_function(f.expr, const_map(f), f.time_dep, 1, map[0], map[1])[0];
       };
       std::vector<int> vol = jac;
-      vol.push_back(mapped(FN_RHS));
+      const int g_node = mapped(FN_RHS);
+      vol.push_back(g_node);
       out.prog_vol = ps.add_point_program(vol, MODE_LINES);
+      out.prog_vol_F = ps.add_point_program(jac, MODE_LINES);
+      out.prog_vol_G = ps.add_point_program({g_node}, MODE_LINES);
       if (problem == 0) {
         if (!need(FN_BC, "micro_bc")) return 1;
         out.prog_bv = ps.add_point_program({mapped(FN_BC)}, MODE_LINES);
@@ -54,18 +57,23 @@ int build_problem_programs(int problem, const FnDef* fn, ProblemPrograms& out, s
       }
       if (fn[FN_SOLUTION].set) out.prog_err = ps.add_point_program({mapped(FN_SOLUTION)}, MODE_POINTS);
       out.jac_depends_on_x = 0;
-      for (int j : jac)
+      out.jac_depends_on_y = 0;
+      for (int j : jac) {
         if (ps.node_dep(j) & DEP_X) out.jac_depends_on_x = 1;
+        if (ps.node_dep(j) & (DEP_Y0 | DEP_Y1)) out.jac_depends_on_y = 1;
+      }
     } else {
       if (!need(FN_RHS, "micro_rhs") || !need(FN_BC_V1, "micro_bc_robin") || !need(FN_BC_V2, "micro_bc_neumann"))
         return 1;
       out.has_map = 0;
       out.jac_depends_on_x = 0;
+      out.jac_depends_on_y = 0;
       auto plain = [&](int slot) {
         const FnDef& f = fn[slot];
         return ps.parse_function(f.expr, const_map(f), f.time_dep, 1)[0];
       };
       out.prog_vol = ps.add_point_program({plain(FN_RHS)}, MODE_LINES);
+      out.prog_vol_G = out.prog_vol;
       // reference boundary ids (rho_solver.cpp:40-50): |y1| = 1 NEUMANN, the rest (|y0| = 1) ROBIN
       const int robin = plain(FN_BC_V1), neumann = plain(FN_BC_V2);
       out.prog_face[0] = ps.add_point_program({robin}, MODE_LINES);

@@ -25,12 +25,15 @@ struct FnDef {
 struct ProblemPrograms {
   ProgramSet ps;
   int prog_vol = -1;             // volume quadrature points: F00 F01 F10 F11 G   (no mapping: G)
+  int prog_vol_F = -1;           // F00 F01 F10 F11 only (run once per cell when F does not depend on y)
+  int prog_vol_G = -1;           // G only
   int prog_bv = -1;              // elliptic Dirichlet data at boundary vertices
   int prog_err = -1;             // exact solution at arbitrary points (MODE_POINTS)
   int prog_init = -1;            // parabolic initial condition at arbitrary points
   int prog_face[4] = {-1, -1, -1, -1};  // sides x=-1, x=+1, y=-1, y=+1: F00..F11 BC   (no mapping: BC)
   int has_map = 0;
   int jac_depends_on_x = 1;
+  int jac_depends_on_y = 1;      // 0: K and det(F) are constant per system, stiffness moments are closed-form
 };
 
 // problem: 0 elliptic, 1 bio, 2 parabolic (msgpu_problem); fn indexed by msgpu_function_slot.

@@ -51,6 +51,8 @@ constexpr int VM_MAX_CONST = 192;
 struct VmProgram {
   int n_code;
   int n_regs;  // per-thread registers the program touches (inputs + outputs + temporaries)
+  int out0;    // first output register of a point program (0 in MODE_LINES, 2 in MODE_POINTS)
+  int pad_;
   uint32_t code[VM_MAX_CODE];
   double consts[VM_MAX_CONST];
 };
@@ -59,7 +61,7 @@ struct VmProgram {
 constexpr int VM_REG_IN0 = 0;  // x0 (slot program) | y0 (line-0 program, MODE_POINTS) | y1 (line-1 program)
 constexpr int VM_REG_IN1 = 1;  // x1 (slot program) | y1 (MODE_POINTS)
 constexpr int VM_REG_IN2 = 2;  // t  (slot program)
-constexpr int VM_REG_OUT0 = 3; // first output register of a point program
+constexpr int VM_REG_TMP0 = 3; // first temporary of the table-building programs
 
 inline constexpr uint32_t vm_encode(uint32_t op, uint32_t kind, uint32_t idx, uint32_t idx2 = 0) {
   return op | (kind << 8) | (idx << 11) | (idx2 << 21);

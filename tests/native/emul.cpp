@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../dealiiscale_b200/csrc/assemble_bodies.cuh"
@@ -32,6 +33,8 @@ struct Emul {
   std::vector<int> iters;
   std::string err;
   int jac_flag = 0;
+  int vector_vm = 1;  // 1: the vectorised moments body (what the product launches for q = 2, 3, 12)
+  std::vector<double> qsum;
   std::vector<double> R;
   Tables tables() const {
     Tables tb;
@@ -43,8 +46,8 @@ struct Emul {
     tb.n1 = pp.ps.n_line1();
     return tb;
   }
-  double* regs(const VmProgram& p) {
-    R.assign(static_cast<size_t>(std::max(8, p.n_regs)) * TBE, 0.0);
+  double* regs(const VmProgram& p, int width = 1) {
+    R.assign(static_cast<size_t>(std::max(8, p.n_regs)) * width * TBE, 0.0);
     return R.data();
   }
 };
@@ -78,6 +81,14 @@ int emul_set_function(void* h, int slot, const char* expr, const char* const* na
   }
   return 0;
 }
+int emul_set_vector_mode(void* h, int on) {
+  static_cast<Emul*>(h)->vector_vm = on;
+  return 0;
+}
+int emul_moment_mode(void* h) {
+  Emul* e = static_cast<Emul*>(h);
+  return !e->pp.has_map ? MODE_NO_MAP : (e->pp.jac_depends_on_y ? MODE_GENERAL : MODE_CONST_F);
+}
 int emul_set_scalars(void* h, const double* v, int n) {
   Emul* e = static_cast<Emul*>(h);
   for (int i = 0; i < n; ++i) e->scalars[i] = v[i];
@@ -107,6 +118,9 @@ int emul_setup(void* h, const double* xy, int N, double t) {
   e->xy.assign(xy, xy + 2 * N);
   gauss_legendre_unit(md.q, e->q1pt, e->q1wt);
   e->qtab = build_qtab(md.q, e->q1pt, e->q1wt);
+  e->qsum.assign(QTAB_STRIDE, 0.0);
+  for (int q = 0; q < md.q * md.q; ++q)
+    for (int i = 0; i < QTAB_STRIDE; ++i) e->qsum[i] += e->qtab[static_cast<size_t>(q) * QTAB_STRIDE + i];
   e->coord0.resize(md.P);
   e->coord1.resize(md.P);
   for (int p = 0; p < md.nc * md.q; ++p) {
@@ -181,7 +195,7 @@ int emul_eval_volume_point(void* h, int k, int cx, int cy, int qx, int qy, doubl
   io.L0 = tb.T0 + static_cast<size_t>(k) * tb.n0 * md.P + cx * md.q + qx;
   io.L1 = tb.T1 + static_cast<size_t>(k) * tb.n1 * md.P + qy * md.nc + cy;
   vm_run(prog, 0, io);
-  for (int i = 0; i < n_out; ++i) out[i] = io.R[(VM_REG_OUT0 + i) * TBE];
+  for (int i = 0; i < n_out; ++i) out[i] = io.R[(prog.out0 + i) * TBE];
   return 0;
 }
 
@@ -202,7 +216,7 @@ int emul_eval_free_point(void* h, int which /*0 err, 1 init*/, int k, double y0,
   io.R[0] = y0;
   io.R[TBE] = y1;
   vm_run(prog, 0, io);
-  *out = io.R[VM_REG_OUT0 * TBE];
+  *out = io.R[prog.out0 * TBE];
   return 0;
 }
 
@@ -214,9 +228,39 @@ int emul_assemble(void* h, const double* u, const double* w) {
   Tables tb = e->tables();
   const double d2 = prob == PF_BIO ? e->scalars[4] : 1.0;
   const VmProgram& vol = ps.point_program(e->pp.prog_vol);
-  for (long long g = 0; g < static_cast<long long>(N) * md.ncells; ++g)
-    body_cell_moments(vol, md, tb, e->qtab.data(), 0, N, d2, e->pp.has_map, e->cell.data(), &e->jac_flag, g,
-                      e->regs(vol), TBE);
+  const VmProgram& volG = ps.point_program(e->pp.prog_vol_G);
+  const VmProgram& volF = e->pp.prog_vol_F >= 0 ? ps.point_program(e->pp.prog_vol_F) : vol;
+  const int mode = emul_moment_mode(e);
+  const TabGlobal tab{e->qtab.data(), e->qsum.data()};
+  const long long work = static_cast<long long>(N) * md.ncells;
+  auto run_vec = [&](auto Qc, auto Wc) {
+    constexpr int Q = decltype(Qc)::value, W = decltype(Wc)::value;
+    for (long long g = 0; g < work; ++g) {
+      if (mode == MODE_GENERAL)
+        body_cell_moments_vec<Q, W, MODE_GENERAL>(vol, vol, md, tb, tab, 0, N, d2, e->cell.data(), &e->jac_flag, g,
+                                                  e->regs(vol, W), TBE);
+      else if (mode == MODE_CONST_F)
+        body_cell_moments_vec<Q, W, MODE_CONST_F>(volF, volG, md, tb, tab, 0, N, d2, e->cell.data(), &e->jac_flag, g,
+                                                  e->regs(volF.n_regs > volG.n_regs * W ? volF : volG,
+                                                          volF.n_regs > volG.n_regs * W ? 1 : W), TBE);
+      else
+        body_cell_moments_vec<Q, W, MODE_NO_MAP>(volG, volG, md, tb, tab, 0, N, d2, e->cell.data(), &e->jac_flag, g,
+                                                 e->regs(volG, W), TBE);
+    }
+  };
+  if (e->vector_vm && md.q == 12) {
+    if (mode == MODE_GENERAL) run_vec(std::integral_constant<int, 12>(), std::integral_constant<int, 6>());
+    else run_vec(std::integral_constant<int, 12>(), std::integral_constant<int, 12>());
+  } else if (e->vector_vm && md.q == 3) {
+    run_vec(std::integral_constant<int, 3>(), std::integral_constant<int, 3>());
+  } else if (e->vector_vm && md.q == 2) {
+    run_vec(std::integral_constant<int, 2>(), std::integral_constant<int, 2>());
+  } else {
+    const VmProgram& sp = e->pp.has_map ? vol : volG;
+    for (long long g = 0; g < work; ++g)
+      body_cell_moments(sp, md, tb, e->qtab.data(), 0, N, d2, e->pp.has_map, e->cell.data(), &e->jac_flag, g,
+                        e->regs(sp), TBE);
+  }
   if (prob != PF_ELLIPTIC)
     for (int s = 0; s < 4; ++s) {
       const VmProgram& fp = ps.point_program(e->pp.prog_face[s]);
