@@ -376,12 +376,14 @@ MSGPU_HOSTDEV void body_gather(const GatherArgs& a, long long gtid) {
       if (right_ok) load += F(side, 3, ix);
     }
   }
-  double* dg = a.diag + static_cast<size_t>(k) * NDIAG * md.ld + r;
-  dg[0] = d0;
-  dg[static_cast<size_t>(1) * md.ld] = d1;
-  dg[static_cast<size_t>(2) * md.ld] = d2;
-  dg[static_cast<size_t>(3) * md.ld] = d3;
-  dg[static_cast<size_t>(4) * md.ld] = d4;
+  if (a.diag != nullptr) {  // parabolic: all systems share one matrix, built once on the host
+    double* dg = a.diag + static_cast<size_t>(k) * NDIAG * md.ld + r;
+    dg[0] = d0;
+    dg[static_cast<size_t>(1) * md.ld] = d1;
+    dg[static_cast<size_t>(2) * md.ld] = d2;
+    dg[static_cast<size_t>(3) * md.ld] = d3;
+    dg[static_cast<size_t>(4) * md.ld] = d4;
+  }
   a.b0[static_cast<size_t>(k) * md.n + r] = load;
   if (a.jw != nullptr) a.jw[static_cast<size_t>(k) * md.n + r] = jw;
 }
@@ -463,6 +465,16 @@ MSGPU_HOSTDEV void body_rhs(const RhsArgs& a, long long gtid) {
     const double* edge = a.edge + static_cast<size_t>(k) * 4 * md.m;
     if (ix == 0) val += a.coef_u * a.u[k] * edge[iy];
     if (ix == md.m - 1) val += a.coef_w * a.w[k] * edge[md.m + iy];
+  } else {
+    // RhoSolver::assemble_system (rho_solver.cpp:138-147, :180-216) with implicit Euler:
+    //   b = M rho_old + dt * (volume load + Robin/Neumann face loads) + dt*kappa*(pi_k + p_F) * int_Robin phi
+    // a.b holds M rho_old on entry; the start vector is zero (rho_solver.cpp:136).
+    const double* edge = a.edge + static_cast<size_t>(k) * 4 * md.m;
+    val = a.b[vo + r] + a.dt * val;
+    const double robin = a.dt * a.coef_u * (a.u[k] + a.coef_w);
+    if (ix == 0) val += robin * edge[iy];
+    if (ix == md.m - 1) val += robin * edge[md.m + iy];
+    a.x[vo + r] = 0.0;
   }
   a.b[vo + r] = val;
 }

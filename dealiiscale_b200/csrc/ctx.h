@@ -56,6 +56,9 @@ struct msgpu_ctx {
   double *d_b = nullptr, *d_x = nullptr, *d_xold = nullptr, *d_u = nullptr, *d_w = nullptr;
   double *d_c = nullptr, *d_res = nullptr, *d_err = nullptr;
   double *d_mass = nullptr, *d_macro = nullptr, *d_lumped = nullptr;  // parabolic: shared mass stencil, lumped weights
+  double *d_cellred = nullptr, *d_eq_pt = nullptr, *d_eq_wt = nullptr;  // error / residual scratch and quadrature
+  int eq_degree = 0;
+  double parabolic_dt = -1.0;
   int *d_iters = nullptr, *d_flags = nullptr;
   size_t bytes_allocated = 0;
 

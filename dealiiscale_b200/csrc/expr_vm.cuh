@@ -129,7 +129,7 @@ MSGPU_HOSTDEV int vm_run(const VmProgram& prog, int pc, const VmIo& io) {
 // Out-of-line wrappers for the expensive functions: the vectorised VM calls them W times per
 // opcode; keeping them out of line keeps the interpreter small enough for the instruction cache.
 #ifdef __CUDACC__
-#define MSGPU_OUTOFLINE __host__ __device__ __noinline__
+#define MSGPU_OUTOFLINE static __host__ __device__ __noinline__
 #else
 #define MSGPU_OUTOFLINE inline
 #endif

@@ -11,6 +11,7 @@
 // depends on (cx, qx) only is warp-uniform and everything that depends on (cy, qy) is
 // unit-stride in memory.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <stdexcept>
 #include <vector>
@@ -100,5 +101,52 @@ inline std::vector<int> reference_numbering(int mesh_kind, int nc) {
   for (int r = 0; r < m * m; ++r) ref_to_internal[internal_to_ref[r]] = r;
   return ref_to_internal;
 }
+
+// parabolic: shared stencils built on the host (n entries, closed-form Q1 local matrices on a
+// square cell: what MatrixCreator::create_mass_matrix / create_laplace_matrix with QGauss(2)
+// integrate exactly, reference src/elliptic-parabolic/rho_solver.cpp:64-65)
+inline void add_local_stencil(std::vector<double>& dg, const MeshDims& md, int cx, int cy, const double loc[4][4], double f) {
+  for (int a = 0; a < 4; ++a)
+    for (int b = a; b < 4; ++b) {
+      const int ra = (cx + (a & 1)) * md.m + (cy + (a >> 1)), rb = (cx + (b & 1)) * md.m + (cy + (b >> 1));
+      const int lo = std::min(ra, rb), off = std::abs(rb - ra);
+      const int d = off == 0 ? 0 : off == 1 ? 1 : off == md.m - 1 ? 2 : off == md.m ? 3 : 4;
+      dg[static_cast<size_t>(d) * md.ld + lo] += f * loc[a][b];
+    }
+}
+
+inline void build_stencils(const MeshDims& md, double dt, double D, double kappa, double R, std::vector<double>& mass,
+                           std::vector<double>& sys, std::vector<double>& lumped) {
+  const double h = md.h;
+  double M[4][4], L[4][4];
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b) {
+      const int sx = (a & 1) == (b & 1), sy = (a >> 1) == (b >> 1);
+      M[a][b] = h * h / 36.0 * (sx ? 2.0 : 1.0) * (sy ? 2.0 : 1.0);
+      L[a][b] = (a == b) ? 4.0 / 6.0 : (sx || sy) ? -1.0 / 6.0 : -2.0 / 6.0;
+    }
+  mass.assign(static_cast<size_t>(NDIAG) * md.ld, 0.0);
+  sys.assign(static_cast<size_t>(NDIAG) * md.ld, 0.0);
+  lumped.assign(md.n, 0.0);
+  for (int cx = 0; cx < md.nc; ++cx)
+    for (int cy = 0; cy < md.nc; ++cy) {
+      add_local_stencil(mass, md, cx, cy, M, 1.0);
+      add_local_stencil(sys, md, cx, cy, M, 1.0);
+      add_local_stencil(sys, md, cx, cy, L, dt * D);
+      for (int a = 0; a < 4; ++a) lumped[(cx + (a & 1)) * md.m + (cy + (a >> 1))] += h * h / 4.0;
+    }
+  // Robin mass kappa*dt*R * int phi_i phi_j on the faces |y0| = 1 (rho_solver.cpp:151-178)
+  const double c = kappa * dt * R * h / 6.0;
+  for (int side = 0; side < 2; ++side) {
+    const int ix = side == 0 ? 0 : md.m - 1;
+    for (int f = 0; f < md.nc; ++f) {
+      const int r = ix * md.m + f;
+      sys[r] += 2.0 * c;
+      sys[r + 1] += 2.0 * c;
+      sys[static_cast<size_t>(1) * md.ld + r] += c;
+    }
+  }
+}
+
 
 }  // namespace msgpu

@@ -88,7 +88,8 @@ struct RhsArgs {
   int N;
   const double* u;      // [N]
   const double* w;      // [N] or null
-  double coef_u, coef_w;  // bio: kappa_1, kappa_3 ; elliptic: 1, 0
+  double coef_u, coef_w;  // bio: kappa_1, kappa_3 ; elliptic: 1, 0 ; parabolic: kappa, p_F
+  double dt;              // parabolic time step
   double* diag;
   const double* b0;
   const double* jw;
@@ -132,6 +133,16 @@ struct CouplingArgs {
   double* c1;
 };
 int launch_coupling(cudaStream_t s, const CouplingArgs& a);
+
+// K8: per-grid error / residual integrals and the point-evaluated load (parabolic initial data) ----
+// cellred: [N][2][ncells] scratch; out2: [N][2] = per-grid sums of the two per-cell quantities
+int launch_cell_errors(cudaStream_t s, const VmProgram& prog, MeshDims md, const double* slots, int n_slots, int qe,
+                       const double* pt, const double* wt, const double* x, int N, double fd, double* cellred,
+                       double* out2);
+int launch_cell_residuals(cudaStream_t s, MeshDims md, const double* x, const double* xold, int N, double* cellred,
+                          double* out2);
+int launch_cell_point_load(cudaStream_t s, const VmProgram& prog, MeshDims md, const double* slots, int n_slots, int qe,
+                           const double* pt, const double* wt, int k0, int nk, double* cell);
 
 // y = M x for the shared symmetric stencil matrix (parabolic K7 building block) ----------------
 int launch_shared_spmv(cudaStream_t s, MeshDims md, int N, const double* diag, const double* x, double* y);

@@ -57,7 +57,7 @@ void free_all(msgpu_ctx* ctx) {
                   ctx->d_q1pt, ctx->d_q1wt,  ctx->d_cell, ctx->d_face, ctx->d_diag,   ctx->d_b0,     ctx->d_jw,
                   ctx->d_edge, ctx->d_bv,    ctx->d_b,   ctx->d_x,    ctx->d_xold,   ctx->d_u,      ctx->d_w,
                   ctx->d_c,    ctx->d_res,   ctx->d_iters, ctx->d_flags, ctx->d_err,  ctx->d_mass,   ctx->d_macro,
-                  ctx->d_lumped};
+                  ctx->d_lumped, ctx->d_cellred, ctx->d_eq_pt, ctx->d_eq_wt};
   for (void* p : ptrs)
     if (p) cudaFree(p);
 }
@@ -134,6 +134,7 @@ int build_tables(msgpu_ctx* ctx, double t) {
 }  // namespace
 
 namespace msgpu {
+int build_tables_at(msgpu_ctx* ctx, double t) { return build_tables(ctx, t); }
 int parabolic_setup(msgpu_ctx* ctx);                       // kernels_extra.cu / parabolic.cu
 int parabolic_assemble(msgpu_ctx* ctx, double dt, double t);
 int compute_errors(msgpu_ctx* ctx, double* l2, double* h1);

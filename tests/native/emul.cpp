@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../dealiiscale_b200/csrc/assemble_bodies.cuh"
+#include "../../dealiiscale_b200/csrc/extra_bodies.cuh"
 #include "../../dealiiscale_b200/csrc/fe_tables.h"
 #include "../../dealiiscale_b200/csrc/problem_programs.h"
 
@@ -28,7 +29,8 @@ struct Emul {
   MeshDims md{};
   int N = 0;
   std::vector<double> xy, slots, T0, T1, coord0, coord1, qtab, q1pt, q1wt;
-  std::vector<double> cell, face, diag, b0, jw, edge, bv, b, x, xold;
+  std::vector<double> cell, face, diag, b0, jw, edge, bv, b, x, xold, mass, lumped;
+  double par_dt = -1;
   std::vector<int> ref_to_internal;
   std::vector<int> iters;
   std::string err;
@@ -330,7 +332,7 @@ int emul_solve(void* h, double tol, int max_it, int* iters_out) {
   std::vector<double> g(n), d(n), hh(n);
   if (e->problem == PF_BIO) e->xold = e->x;
   for (int k = 0; k < e->N; ++k) {
-    const double* dg = e->diag.data() + static_cast<size_t>(k) * NDIAG * md.ld;
+    const double* dg = e->diag.data() + (e->problem == PF_PARABOLIC ? 0 : static_cast<size_t>(k) * NDIAG * md.ld);
     double* x = e->x.data() + static_cast<size_t>(k) * n;
     const double* b = e->b.data() + static_cast<size_t>(k) * n;
     spmv5(md, dg, x, hh.data());
@@ -398,7 +400,7 @@ int emul_get_matrix_dense(void* h, int k, double* out) {
   Emul* e = static_cast<Emul*>(h);
   const MeshDims& md = e->md;
   const size_t n = md.n;
-  const double* dg = e->diag.data() + static_cast<size_t>(k) * NDIAG * md.ld;
+  const double* dg = e->diag.data() + (e->problem == PF_PARABOLIC ? 0 : static_cast<size_t>(k) * NDIAG * md.ld);
   std::vector<int> internal_to_ref(n);
   for (size_t i = 0; i < n; ++i) internal_to_ref[e->ref_to_internal[i]] = static_cast<int>(i);
   std::fill(out, out + n * n, 0.0);
@@ -453,6 +455,158 @@ int emul_coupling(void* h, double* c0, double* c1) {
       for (int r = 0; r < md.n; ++r) s += x[r] * jw[r];
       c0[k] = s;
     }
+  }
+  return 0;
+}
+
+
+// ---- errors / residuals (same bodies as kernels_extra.cu, sequential) ---------------------------
+int emul_errors(void* h, double* l2, double* h1) {
+  Emul* e = static_cast<Emul*>(h);
+  if (e->pp.prog_err < 0) return 1;
+  const MeshDims& md = e->md;
+  const int qe = e->problem == PF_PARABOLIC ? 3 : md.q;
+  std::vector<double> pt, wt;
+  gauss_legendre_unit(qe, pt, wt);
+  const VmProgram& prog = e->pp.ps.point_program(e->pp.prog_err);
+  std::vector<double> red(static_cast<size_t>(e->N) * 2 * md.ncells);
+  for (long long g = 0; g < static_cast<long long>(e->N) * md.ncells; ++g)
+    body_cell_errors(prog, md, e->slots.data(), e->pp.ps.n_slots(), qe, pt.data(), wt.data(), e->x.data(), e->N, 1e-8,
+                     red.data(), g, e->regs(prog), TBE);
+  for (int k = 0; k < e->N; ++k) {
+    double a = 0, b = 0;
+    for (int c = 0; c < md.ncells; ++c) {
+      a += red[(static_cast<size_t>(k) * 2) * md.ncells + c];
+      b += red[(static_cast<size_t>(k) * 2 + 1) * md.ncells + c];
+    }
+    l2[k] = std::sqrt(a);
+    h1[k] = std::sqrt(e->problem == PF_PARABOLIC ? a + b : b);
+  }
+  return 0;
+}
+int emul_residuals(void* h, double* l2) {
+  Emul* e = static_cast<Emul*>(h);
+  const MeshDims& md = e->md;
+  std::vector<double> red(static_cast<size_t>(e->N) * 2 * md.ncells);
+  for (long long g = 0; g < static_cast<long long>(e->N) * md.ncells; ++g)
+    body_cell_residual(md, e->x.data(), e->xold.data(), e->N, red.data(), g);
+  for (int k = 0; k < e->N; ++k) {
+    double a = 0;
+    for (int c = 0; c < md.ncells; ++c) a += red[(static_cast<size_t>(k) * 2) * md.ncells + c];
+    l2[k] = std::sqrt(a);
+  }
+  return 0;
+}
+
+// ---- parabolic: mirrors parabolic_setup / parabolic_assemble of kernels_extra.cu ---------------
+static void rebuild_tables(Emul* e, double t) {
+  const MeshDims& md = e->md;
+  const ProgramSet& ps = e->pp.ps;
+  const int N = e->N;
+  if (ps.n_slots() > 0)
+    for (long long g = 0; g < N; ++g)
+      body_slots(ps.slot_program(), e->xy.data(), N, t, e->slots.data(), ps.n_slots(), g, e->regs(ps.slot_program()), TBE);
+  if (ps.n_line0() + ps.n_line1() > 0) {
+    const VmProgram& big = ps.line0_program().n_regs > ps.line1_program().n_regs ? ps.line0_program() : ps.line1_program();
+    for (long long g = 0; g < static_cast<long long>(N) * md.P; ++g)
+      body_lines(ps.line0_program(), ps.line1_program(), e->coord0.data(), e->coord1.data(), md.P, N, e->slots.data(),
+                 ps.n_slots(), e->T0.data(), ps.n_line0(), e->T1.data(), ps.n_line1(), g, e->regs(big), TBE);
+  }
+}
+int emul_parabolic_init(void* h) {
+  Emul* e = static_cast<Emul*>(h);
+  const MeshDims& md = e->md;
+  const int N = e->N;
+  std::vector<double> sys;
+  build_stencils(md, 0.0, e->scalars[3], e->scalars[0], e->scalars[2], e->mass, sys, e->lumped);
+  if (e->pp.prog_init < 0) return 0;
+  std::vector<double> pt, wt;
+  gauss_legendre_unit(3, pt, wt);
+  const VmProgram& prog = e->pp.ps.point_program(e->pp.prog_init);
+  for (long long g = 0; g < static_cast<long long>(N) * md.ncells; ++g)
+    body_cell_point_load(prog, md, e->slots.data(), e->pp.ps.n_slots(), 3, pt.data(), wt.data(), 0, N, e->cell.data(), g,
+                         e->regs(prog), TBE);
+  GatherArgs ga{};
+  ga.md = md;
+  ga.problem = PF_PARABOLIC;
+  ga.k0 = 0;
+  ga.nk = N;
+  ga.cell = e->cell.data();
+  ga.face = nullptr;
+  ga.diag = nullptr;
+  ga.b0 = e->b.data();
+  ga.jw = nullptr;
+  ga.edge = e->edge.data();
+  for (long long g = 0; g < static_cast<long long>(N) * md.n; ++g) body_gather(ga, g);
+  e->diag = e->mass;
+  std::fill(e->x.begin(), e->x.end(), 0.0);
+  emul_solve(h, 1e-14, 10 * md.n + 100, nullptr);
+  e->xold = e->x;
+  return 0;
+}
+int emul_parabolic_step(void* h, const double* u, double dt, double t, double tol, int max_it, int* iters) {
+  Emul* e = static_cast<Emul*>(h);
+  const MeshDims& md = e->md;
+  const ProgramSet& ps = e->pp.ps;
+  const int N = e->N;
+  const double kappa = e->scalars[0], p_F = e->scalars[1], R = e->scalars[2], D = e->scalars[3];
+  std::vector<double> mass;
+  build_stencils(md, dt, D, kappa, R, mass, e->diag, e->lumped);
+  rebuild_tables(e, t);
+  Tables tb = e->tables();
+  const VmProgram& volG = ps.point_program(e->pp.prog_vol_G);
+  const TabGlobal tab{e->qtab.data(), e->qsum.data()};
+  for (long long g = 0; g < static_cast<long long>(N) * md.ncells; ++g) {
+    if (md.q == 2)
+      body_cell_moments_vec<2, 2, MODE_NO_MAP>(volG, volG, md, tb, tab, 0, N, 1.0, e->cell.data(), &e->jac_flag, g,
+                                               e->regs(volG, 2), TBE);
+    else
+      body_cell_moments(volG, md, tb, e->qtab.data(), 0, N, 1.0, 0, e->cell.data(), &e->jac_flag, g, e->regs(volG), TBE);
+  }
+  for (int s = 0; s < 4; ++s) {
+    const VmProgram& fp = ps.point_program(e->pp.prog_face[s]);
+    for (long long g = 0; g < static_cast<long long>(N) * md.nc; ++g)
+      body_face_moments(fp, s, md, tb, e->q1pt.data(), e->q1wt.data(), 0, N, 0, e->face.data(), g, e->regs(fp), TBE);
+  }
+  GatherArgs ga{};
+  ga.md = md;
+  ga.problem = PF_PARABOLIC;
+  ga.k0 = 0;
+  ga.nk = N;
+  ga.cell = e->cell.data();
+  ga.face = e->face.data();
+  ga.diag = nullptr;
+  ga.b0 = e->b0.data();
+  ga.jw = nullptr;
+  ga.edge = e->edge.data();
+  for (long long g = 0; g < static_cast<long long>(N) * md.n; ++g) body_gather(ga, g);
+  for (int k = 0; k < N; ++k)
+    spmv5(md, e->mass.data(), e->xold.data() + static_cast<size_t>(k) * md.n, e->b.data() + static_cast<size_t>(k) * md.n);
+  RhsArgs ra{};
+  ra.md = md;
+  ra.problem = PF_PARABOLIC;
+  ra.N = N;
+  ra.u = u;
+  ra.w = u;
+  ra.coef_u = kappa;
+  ra.coef_w = p_F;
+  ra.dt = dt;
+  ra.diag = e->diag.data();
+  ra.b0 = e->b0.data();
+  ra.edge = e->edge.data();
+  ra.b = e->b.data();
+  ra.x = e->x.data();
+  for (long long g = 0; g < static_cast<long long>(N) * md.n; ++g) body_rhs(ra, g);
+  int rc = emul_solve(h, tol, max_it, iters);
+  e->xold = e->x;
+  return rc;
+}
+int emul_mass_integrals(void* h, double* c0) {
+  Emul* e = static_cast<Emul*>(h);
+  for (int k = 0; k < e->N; ++k) {
+    double s = 0;
+    for (int r = 0; r < e->md.n; ++r) s += e->x[static_cast<size_t>(k) * e->md.n + r] * e->lumped[r];
+    c0[k] = s;
   }
   return 0;
 }
