@@ -1,0 +1,275 @@
+// solve_biomath: bio-multiscale driver on top of the GPU micro path.
+// Host mirror of reference src/bio-multiscale/{macro,manager}.{h,cpp} and manufactured.cpp.
+#pragma once
+#include <chrono>
+#include <cstdio>
+#include <fstream>
+
+#include "micro_solver.h"
+
+namespace ms {
+namespace bio {
+
+struct Functions {
+  BioData data;
+  MacroFunction solution_u, bulk_rhs_u, bc_u_1, bc_u_2, inflow_measure, outflow_measure;
+  MacroFunction solution_w, bulk_rhs_w, bc_w_1, bc_w_2;
+  explicit Functions(const std::string& file) : data(file) {
+    auto init = [&](MacroFunction& f, const char* key) { f.initialize(data.params.get(key), data.constants); };
+    init(solution_u, "solution_u"); init(bulk_rhs_u, "bulk_rhs_u"); init(bc_u_1, "bc_u_1"); init(bc_u_2, "bc_u_2");
+    init(inflow_measure, "inflow_measure"); init(outflow_measure, "outflow_measure");
+    init(solution_w, "solution_w"); init(bulk_rhs_w, "bulk_rhs_w"); init(bc_w_1, "bc_w_1"); init(bc_w_2, "bc_w_2");
+  }
+};
+
+// reference: macro.{h,cpp}
+class MacroSolver {
+ public:
+  MacroSolver(Functions& f, unsigned int n_cells) : pde_data(f), n_cells(n_cells) {}
+  void setup() {  // macro.cpp:36-86: |x1| = 1 faces NEUMANN, |x0| = 1 faces DIRICHLET
+    mesh.build(MSGPU_MESH_SUBDIVIDED, n_cells);
+    system_matrix_u.reinit(mesh);
+    system_matrix_w.reinit(mesh);
+    for (auto* v : {&sol_u, &sol_w, &old_sol_u, &old_sol_w, &system_rhs_u, &system_rhs_w, &micro_contribution_u,
+                    &micro_contribution_w})
+      v->assign(mesh.n, 0.0);
+  }
+  void get_dof_locations(std::vector<std::array<double, 2>>& loc) const {
+    loc.resize(mesh.n);
+    for (int d = 0; d < mesh.n; ++d) loc[d] = {mesh.x_of(d), mesh.y_of(d)};
+  }
+  void set_micro_objects(MicroSolver* m) { micro = m; }
+  // integrate_micro_cells for every macro DoF (macro.cpp:254-306): one coupling kernel
+  void compute_microscopic_contribution() { micro->coupling(micro_contribution_u, &micro_contribution_w); }
+  void assemble_system() {  // macro.cpp:100-192
+    system_matrix_u.zero();
+    system_matrix_w.zero();
+    std::fill(system_rhs_u.begin(), system_rhs_u.end(), 0.0);
+    std::fill(system_rhs_w.begin(), system_rhs_w.end(), 0.0);
+    compute_microscopic_contribution();
+    Quadrature Q(8);
+    const double h = mesh.h;
+    const double k_1 = pde_data.data.constants.at("kappa_1"), k_3 = pde_data.data.constants.at("kappa_3");
+    const double D_1 = pde_data.data.constants.at("D_1");
+    for (size_t c = 0; c < mesh.cell_dofs.size(); ++c) {
+      const auto& cd = mesh.cell_dofs[c];
+      const int cx = mesh.cell_cx[c], cy = mesh.cell_cy[c];
+      const double ox = -1.0 + cx * h, oy = -1.0 + cy * h;
+      double Au[4][4] = {}, Aw[4][4] = {}, bu[4] = {}, bw[4] = {};
+      for (int j = 0; j < 8; ++j)
+        for (int i = 0; i < 8; ++i) {
+          double v[4], g[4][2];
+          shape(Q.pt[i], Q.pt[j], v);
+          shape_grad(Q.pt[i], Q.pt[j], h, g);
+          const double jxw = Q.wt[i] * Q.wt[j] * h * h;
+          const double x0 = ox + h * Q.pt[i], x1 = oy + h * Q.pt[j];
+          double uc = 0, wc = 0;
+          for (int a = 0; a < 4; ++a) {
+            uc += micro_contribution_u[cd[a]] * v[a];
+            wc += micro_contribution_w[cd[a]] * v[a];
+          }
+          const double infl = pde_data.inflow_measure.value(x0, x1), outfl = pde_data.outflow_measure.value(x0, x1);
+          const double fu = pde_data.bulk_rhs_u.value(x0, x1), fw = pde_data.bulk_rhs_w.value(x0, x1);
+          for (int a = 0; a < 4; ++a) {
+            for (int b = 0; b < 4; ++b) {
+              const double laplace_term = (g[a][0] * g[b][0] + g[a][1] * g[b][1]) * jxw;
+              const double mass_term = v[a] * v[b] * jxw;
+              Au[a][b] += laplace_term + mass_term * k_1 * infl;
+              Aw[a][b] += D_1 * laplace_term + mass_term * k_3 * outfl;
+            }
+            bu[a] += (-uc + fu) * v[a] * jxw;
+            bw[a] += (-wc + fw) * v[a] * jxw;
+          }
+        }
+      // boundary faces: 0 x-min, 1 x-max (DIRICHLET id), 2 y-min, 3 y-max (NEUMANN id)
+      const bool at[4] = {cx == 0, cx == (int)n_cells - 1, cy == 0, cy == (int)n_cells - 1};
+      for (int f = 0; f < 4; ++f) {
+        if (!at[f]) continue;
+        for (int q = 0; q < 8; ++q) {
+          const double s = Q.pt[q];
+          const double xi = f == 0 ? 0 : f == 1 ? 1 : s, eta = f == 2 ? 0 : f == 3 ? 1 : s;
+          double v[4];
+          shape(xi, eta, v);
+          const double jxw = Q.wt[q] * h, x0 = ox + h * xi, x1 = oy + h * eta;
+          for (int a = 0; a < 4; ++a) {
+            if (f >= 2) {
+              bu[a] += v[a] * jxw * pde_data.bc_u_2.value(x0, x1);
+              bw[a] += v[a] * jxw * pde_data.bc_w_2.value(x0, x1);
+            } else {
+              bw[a] += v[a] * jxw * pde_data.bc_w_1.value(x0, x1);
+            }
+          }
+        }
+      }
+      for (int a = 0; a < 4; ++a) {
+        for (int b = 0; b < 4; ++b) {
+          system_matrix_u.add(cd[a], cd[b], Au[a][b]);
+          system_matrix_w.add(cd[a], cd[b], Aw[a][b]);
+        }
+        system_rhs_u[cd[a]] += bu[a];
+        system_rhs_w[cd[a]] += bw[a];
+      }
+    }
+    std::map<int, double> boundary_values;  // u only, on |x0| = 1 (macro.cpp:189-191)
+    for (int d = 0; d < mesh.n; ++d)
+      if (mesh.dof_ix[d] == 0 || mesh.dof_ix[d] == mesh.m - 1)
+        boundary_values[d] = pde_data.bc_u_1.value(mesh.x_of(d), mesh.y_of(d));
+    apply_boundary_values(boundary_values, system_matrix_u, sol_u, system_rhs_u);
+  }
+  void solve() {  // macro.cpp:194-202
+    old_sol_u = sol_u;
+    old_sol_w = sol_w;
+    solve_cg(system_matrix_u, sol_u, system_rhs_u, 10000, 1e-12);
+    solve_cg(system_matrix_w, sol_w, system_rhs_w, 10000, 1e-12);
+  }
+  void assemble_and_solve() {
+    assemble_system();
+    solve();
+  }
+  void compute_error(double& l2_error, double& h1_error) const {  // macro.cpp:204-228
+    double lu, hu, lw, hw;
+    field_errors(mesh, sol_u, pde_data.solution_u, 8, lu, hu);
+    field_errors(mesh, sol_w, pde_data.solution_w, 8, lw, hw);
+    l2_error = lu + lw;
+    h1_error = hu + hw;
+  }
+  void compute_residual(double& l2_residual) const {  // macro.cpp:230-245: the u part is overwritten by the w part
+    std::vector<double> e(mesh.n);
+    for (int i = 0; i < mesh.n; ++i) e[i] = sol_w[i] - old_sol_w[i];
+    l2_residual = nodal_l2_norm(mesh, e, 8);
+  }
+
+  MacroMesh mesh;
+  std::vector<double> sol_u, sol_w, old_sol_u, old_sol_w, micro_contribution_u, micro_contribution_w;
+
+ private:
+  Functions& pde_data;
+  unsigned int n_cells;
+  CsrMatrix system_matrix_u, system_matrix_w;
+  std::vector<double> system_rhs_u, system_rhs_w;
+  MicroSolver* micro = nullptr;
+};
+
+struct CycleRecord {
+  int cycle;
+  double mL2 = 0, mH1 = 0, ML2 = 0, MH1 = 0, macro_residual = 0, micro_residual = 0;
+  std::vector<double> sol_u, sol_w, contribution_u, contribution_w, micro_solutions;
+  std::vector<int> micro_iterations;
+};
+
+// reference: manager.{h,cpp}
+class Manager {
+ public:
+  Manager(unsigned int macro_cells, unsigned int micro_cells, const std::string& data_file,
+          const std::string& out_file, int num_threads = 0, int device = -1)
+      : functions(data_file),
+        macro_solver(functions, macro_cells),
+        micro_solver(MSGPU_BIO, micro_cells, 12, MSGPU_MESH_SUBDIVIDED, device),
+        num_threads(num_threads),
+        ct_file_name(out_file) {
+    std::printf("Running elliptic-elliptic solver with data from %s, storing results in %s\n", data_file.c_str(),
+                out_file.c_str());
+    const auto& p = functions.data.params;
+    const Constants& c = functions.data.constants;
+    micro_solver.set_function(MSGPU_FN_MAPPING, p.get("mapping"), c);
+    micro_solver.set_function(MSGPU_FN_JACOBIAN, p.get("jac_mapping"), c);
+    micro_solver.set_function(MSGPU_FN_RHS, p.get("bulk_rhs_v"), c);
+    micro_solver.set_function(MSGPU_FN_SOLUTION, p.get("solution_v"), c);
+    micro_solver.set_function(MSGPU_FN_BC_V1, p.get("bc_v_1"), c);
+    micro_solver.set_function(MSGPU_FN_BC_V2, p.get("bc_v_2"), c);
+    micro_solver.set_function(MSGPU_FN_BC_V3, p.get("bc_v_3"), c);
+    micro_solver.set_function(MSGPU_FN_BC_V4, p.get("bc_v_4"), c);
+    micro_solver.set_scalars(functions.data.scalars());
+  }
+  void setup() {  // manager.cpp:23-49
+    macro_solver.setup();
+    std::vector<std::array<double, 2>> dof_locations;
+    macro_solver.get_dof_locations(dof_locations);
+    micro_solver.set_grid_locations(dof_locations);
+    micro_solver.setup();
+    micro_solver.set_macro_solution(&macro_solver.sol_u, &macro_solver.sol_w);
+    macro_solver.set_micro_objects(&micro_solver);
+    cycle = 0;
+    old_residual = 0;
+    residual = 1;
+    old_error = 0;
+    error = 1;
+  }
+  void run() {  // manager.cpp:51-63
+    bool reached = false;
+    while (!reached) {
+      fixed_point_iterate();
+      check_fixed_point_reached(reached);
+      cycle++;
+      if (cycle > max_iterations) {
+        std::printf("Residual too high after %d iterations, stopping\n", cycle);
+        break;
+      }
+      if (cycle_limit >= 0 && cycle >= cycle_limit) break;
+    }
+    output_results();
+  }
+  std::string convergence_table() const {
+    std::vector<std::vector<std::string>> rows;
+    for (const auto& r : history)
+      rows.push_back({std::to_string(r.cycle), std::to_string(macro_solver.mesh.cell_dofs.size()),
+                      std::to_string(macro_solver.mesh.n), sci3(r.mL2), sci3(r.mH1), sci3(r.ML2), sci3(r.MH1)});
+    return format_table({"cycle", "cells", "dofs", "mL2", "mH1", "ML2", "MH1"}, rows);
+  }
+  void output_results() {  // manager.cpp:111-123 (VTK output of :125-178 is not reproduced)
+    if (!functions.data.params.get_bool("has_solution") || ct_file_name.empty()) return;
+    std::ofstream out(ct_file_name, std::ios::app);
+    out << convergence_table();
+  }
+
+  Functions functions;
+  MacroSolver macro_solver;
+  MicroSolver micro_solver;
+  int num_threads;
+  double old_residual = 0, residual = 1, old_error = 0, error = 1;
+  double error_eps = 1e-2, residual_eps = 1e-5, max_iterations = 1e4;
+  int cycle_limit = -1;
+  bool keep_solutions = false;
+  std::vector<CycleRecord> history;
+
+ private:
+  int cycle = 0;
+  std::string ct_file_name;
+  void fixed_point_iterate() {  // manager.cpp:65-68
+    macro_solver.assemble_and_solve();
+    micro_solver.assemble_and_solve_all();
+  }
+  void check_fixed_point_reached(bool& reached) {  // manager.cpp:70-109
+    CycleRecord r;
+    r.cycle = cycle;
+    if (functions.data.params.get_bool("has_solution")) {
+      macro_solver.compute_error(r.ML2, r.MH1);
+      micro_solver.compute_all_errors(macro_solver.mesh, 12, r.mL2, r.mH1);
+      old_error = error;
+      std::printf("Macro error: %.2e\tMicro error: %.2e\n", r.ML2, r.mL2);
+      error = r.mL2 + r.ML2;
+      std::printf("Old error %.2e, new error %.2e\n", old_error, error);
+      reached = std::fabs(old_error - error) / error < error_eps;
+    } else {
+      macro_solver.compute_residual(r.macro_residual);
+      micro_solver.compute_all_residuals(macro_solver.mesh, 12, r.micro_residual);
+      old_residual = residual;
+      std::printf("Macro residual: %.2e\tMicro residual: %.2e\n", r.macro_residual, r.micro_residual);
+      residual = r.macro_residual + r.micro_residual;
+      std::printf("Old residual %.2e, new residual %.2e\n", old_residual, residual);
+      reached = std::fabs(old_residual - residual) < residual_eps;
+    }
+    r.contribution_u = macro_solver.micro_contribution_u;
+    r.contribution_w = macro_solver.micro_contribution_w;
+    r.micro_iterations = micro_solver.iterations;
+    if (keep_solutions) {
+      r.sol_u = macro_solver.sol_u;
+      r.sol_w = macro_solver.sol_w;
+      micro_solver.all_solutions(r.micro_solutions);
+    }
+    history.push_back(std::move(r));
+  }
+};
+
+}  // namespace bio
+}  // namespace ms

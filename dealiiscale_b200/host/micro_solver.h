@@ -1,0 +1,158 @@
+// MicroSolver: the reference's micro-solver interface, backed by libmsgpu through its C ABI.
+//
+// Same public surface as the reference classes (src/elliptic-elliptic/micro.h:54-98,
+// src/bio-multiscale/micro.h:66-104, src/elliptic-parabolic/rho_solver.h:53-100):
+// set_grid_locations, setup, set_macro_solution, run / assemble_and_solve_all / iterate,
+// compute_all_errors, compute_all_residuals, get_num_grids, solutions.  The reference borrows
+// pointers to the macro vectors and reads them at every run(); so does this class — the
+// values are shipped to the device when run() starts.  There is no CPU fallback: if the CUDA
+// library cannot create a context the constructor throws.
+#pragma once
+#include <array>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/msgpu.h"
+#include "macro_fem.h"
+#include "prm.h"
+
+namespace ms {
+
+class MicroSolver {
+ public:
+  MicroSolver(int problem, int cells_per_axis, int q_degree, int mesh_kind, int device = -1)
+      : problem_(problem), cells_(cells_per_axis) {
+    msgpu_desc d{problem, mesh_kind, cells_per_axis, q_degree, device};
+    const int rc = msgpu_create(&ctx_, &d);
+    if (rc != MSGPU_OK) throw std::runtime_error("msgpu_create failed: no usable CUDA device (there is no CPU fallback)");
+    n_dofs_ = (cells_per_axis + 1) * (cells_per_axis + 1);
+  }
+  ~MicroSolver() { msgpu_destroy(ctx_); }
+  MicroSolver(const MicroSolver&) = delete;
+  MicroSolver& operator=(const MicroSolver&) = delete;
+
+  void set_function(int slot, const std::string& expr, const Constants& c, bool time_dependent = false) {
+    std::vector<const char*> names;
+    std::vector<double> values;
+    for (const auto& kv : c) {
+      names.push_back(kv.first.c_str());
+      values.push_back(kv.second);
+    }
+    check(msgpu_set_function(ctx_, slot, expr.c_str(), names.data(), values.data(), static_cast<int>(names.size()),
+                             time_dependent));
+  }
+  void set_scalars(const std::vector<double>& v) { check(msgpu_set_scalars(ctx_, v.data(), static_cast<int>(v.size()))); }
+
+  // ---- the reference interface ----
+  void set_grid_locations(const std::vector<std::array<double, 2>>& locations) {
+    num_grids_ = static_cast<int>(locations.size());
+    check(msgpu_set_grid_locations(ctx_, &locations[0][0], num_grids_));
+  }
+  void setup() { check(msgpu_setup(ctx_)); }
+  void set_macro_solution(const std::vector<double>* u, const std::vector<double>* w = nullptr) {
+    macro_u_ = u;
+    macro_w_ = w;
+  }
+  unsigned int get_num_grids() const { return num_grids_; }
+  int n_dofs() const { return n_dofs_; }
+
+  void assemble_system() {
+    push_macro();
+    check(msgpu_assemble(ctx_));
+  }
+  void solve() {
+    iterations.assign(num_grids_, 0);
+    check(msgpu_solve(ctx_, 1e-12, problem_ == MSGPU_ELLIPTIC ? 1000 : 10000, MSGPU_PRECOND_IDENTITY, iterations.data(),
+                      nullptr));
+  }
+  void run() {  // micro.cpp:218-221
+    assemble_system();
+    solve();
+  }
+  void assemble_and_solve_all() { run(); }  // bio micro.cpp:292-305
+  void iterate(double dt, double t) {       // rho_solver.cpp:232-237
+    push_macro();
+    iterations.assign(num_grids_, 0);
+    check(msgpu_time_step(ctx_, dt, t, 1e-12, 10000, iterations.data()));
+  }
+  // MacroSolver::compute_microscopic_contribution reads these
+  void coupling(std::vector<double>& c0, std::vector<double>* c1 = nullptr) {
+    c0.assign(num_grids_, 0.0);
+    std::vector<double> dummy(num_grids_);
+    if (c1) c1->assign(num_grids_, 0.0);
+    check(msgpu_coupling(ctx_, c0.data(), c1 ? c1->data() : dummy.data()));
+  }
+  // per-grid norms; the aggregation over the macro mesh is done by the caller (micro.cpp:206-214)
+  void grid_errors(std::vector<double>& l2, std::vector<double>& h1) {
+    l2.assign(num_grids_, 0.0);
+    h1.assign(num_grids_, 0.0);
+    check(msgpu_errors(ctx_, l2.data(), h1.data()));
+  }
+  void grid_residuals(std::vector<double>& l2) {
+    l2.assign(num_grids_, 0.0);
+    check(msgpu_residuals(ctx_, l2.data()));
+  }
+  void compute_all_errors(const MacroMesh& macro_mesh, int q, double& l2_error, double& h1_error) {
+    std::vector<double> l2, h1;
+    grid_errors(l2, h1);
+    l2_error = nodal_l2_norm(macro_mesh, l2, q);
+    h1_error = nodal_l2_norm(macro_mesh, h1, q);
+  }
+  void compute_all_residuals(const MacroMesh& macro_mesh, int q, double& l2_residual) {
+    std::vector<double> r;
+    grid_residuals(r);
+    l2_residual = nodal_l2_norm(macro_mesh, r, q);
+  }
+  // `solutions` of the reference (micro.h:97), reference DoF numbering
+  std::vector<double> solution(int k) {
+    std::vector<double> out(n_dofs_);
+    check(msgpu_get_solutions(ctx_, k, k + 1, out.data()));
+    return out;
+  }
+  void all_solutions(std::vector<double>& out) {
+    out.assign(static_cast<size_t>(num_grids_) * n_dofs_, 0.0);
+    check(msgpu_get_solutions(ctx_, 0, num_grids_, out.data()));
+  }
+  msgpu_ctx* context() { return ctx_; }
+  std::vector<int> iterations;  // CG steps of every grid in the last solve
+
+ private:
+  msgpu_ctx* ctx_ = nullptr;
+  int problem_, cells_, n_dofs_ = 0, num_grids_ = 0;
+  const std::vector<double>*macro_u_ = nullptr, *macro_w_ = nullptr;
+  void push_macro() {
+    if (!macro_u_) throw std::runtime_error("set_macro_solution was not called");
+    check(msgpu_set_macro_solution(ctx_, macro_u_->data(), macro_w_ ? macro_w_->data() : nullptr));
+  }
+  void check(int rc) {
+    if (rc != MSGPU_OK) throw std::runtime_error(std::string("msgpu: ") + msgpu_last_error(ctx_));
+  }
+};
+
+// deal.II ConvergenceTable::write_text (table_with_headers): centred keys, right-aligned entries.
+inline std::string format_table(const std::vector<std::string>& keys, const std::vector<std::vector<std::string>>& rows) {
+  std::vector<size_t> width(keys.size());
+  for (size_t c = 0; c < keys.size(); ++c) {
+    width[c] = keys[c].size();
+    for (const auto& r : rows) width[c] = std::max(width[c], r[c].size());
+  }
+  std::string out;
+  for (size_t c = 0; c < keys.size(); ++c) {
+    const size_t front = (width[c] - keys[c].size()) / 2, back = width[c] - keys[c].size() - front;
+    out += std::string(front, ' ') + keys[c] + std::string(back, ' ') + " ";
+  }
+  out += "\n";
+  for (const auto& r : rows) {
+    for (size_t c = 0; c < keys.size(); ++c) out += std::string(width[c] - r[c].size(), ' ') + r[c] + " ";
+    out += "\n";
+  }
+  return out;
+}
+inline std::string sci3(double v) {
+  char buf[32];
+  std::snprintf(buf, sizeof buf, "%.3e", v);
+  return buf;
+}
+
+}  // namespace ms

@@ -1,0 +1,40 @@
+// solve_biomath [input.prm [macro_refinement [micro_refinement [num_threads]]]] — same command line
+// and timing line as the reference (manufactured.cpp:39-90).  num_threads is accepted for
+// compatibility; the micro path runs on the GPU.
+#include <chrono>
+#include <ctime>
+#include <regex>
+
+#include "bio.h"
+
+int main(int argc, char* argv[]) {
+  std::string input_path = "input/linear.prm";
+  int macro_refinement = 2, micro_refinement = 4, num_threads = 0;
+  if (argc >= 2) input_path = argv[1];
+  if (argc >= 3) macro_refinement = std::stoi(argv[2]);
+  if (argc >= 4) micro_refinement = std::stoi(argv[3]);
+  if (argc >= 5) num_threads = std::stoi(argv[4]);
+  const auto wall0 = std::chrono::steady_clock::now();
+  const std::clock_t cpu0 = std::clock();
+  const std::string output_path = "results/out.txt";
+  { std::ofstream truncate(output_path, std::ios::trunc); }
+  try {
+    ms::bio::Manager manager(1u << macro_refinement, 1u << micro_refinement, input_path, output_path, num_threads);
+    manager.setup();
+    manager.run();
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "solve_biomath: %s\n", e.what());
+    return 2;
+  }
+  const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+  const double cpu = double(std::clock() - cpu0) / CLOCKS_PER_SEC;
+  std::printf("Results: 'macro_refinement', 'micro_refinement', 'num_threads', 'wall_time', 'cpu_time'\n");
+  std::printf("%d, %d, %d, %.3f, %.3f\n", macro_refinement, micro_refinement, num_threads, wall, cpu);
+  if (num_threads != 0) {
+    std::smatch m;
+    const std::string id = std::regex_search(input_path, m, std::regex("input/(.+).prm")) ? m[1].str() : "run";
+    std::ofstream t("results/" + id + "_timings.txt", std::ios::app);
+    t << num_threads << "\t" << wall << "\t" << cpu << std::endl;
+  }
+  return 0;
+}

@@ -1,0 +1,31 @@
+// solve_elliptic [input/<id>.prm] — same command line as the reference (manufactured.cpp:29-40):
+// levels i = 2..5 with (macro refinement i-1, micro refinement i), table appended to
+// results/<id>_convergence_table.txt.
+#include <regex>
+
+#include "elliptic.h"
+
+int main(int argc, char* argv[]) {
+  std::string input_path = "input/map_test.prm";
+  if (argc == 2) {
+    input_path = argv[1];
+  } else if (argc > 2) {
+    std::printf("Too many arguments\n");
+    return 1;
+  }
+  std::smatch m;
+  const std::string id = std::regex_search(input_path, m, std::regex("input/(.+).prm")) ? m[1].str() : "run";
+  const std::string output_path = "results/" + id + "_convergence_table.txt";
+  { std::ofstream truncate(output_path, std::ios::trunc); }
+  try {
+    for (unsigned int i = 2; i < 6; i++) {
+      ms::elliptic::Manager manager(i - 1, i, input_path, output_path);
+      manager.setup();
+      manager.run();
+    }
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "solve_elliptic: %s\n", e.what());
+    return 2;
+  }
+  return 0;
+}

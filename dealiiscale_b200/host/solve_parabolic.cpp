@@ -1,0 +1,30 @@
+// solve_parabolic [input/<id>.prm] — same command line as the reference (two_scale.cpp:16-33, :77-92):
+// seven space-time refinement levels h_inv = round(8*2^(i/2)), t_inv = 4*2^i.
+#include <cmath>
+#include <regex>
+
+#include "parabolic.h"
+
+int main(int argc, char* argv[]) {
+  std::string input_path = "input/full_nonlinear.prm";
+  int levels = 7;
+  if (argc >= 2) input_path = argv[1];
+  if (argc >= 3) levels = std::stoi(argv[2]);  // extension: fewer sweep levels
+  std::smatch m;
+  const std::string id = std::regex_search(input_path, m, std::regex("input/(.+).prm")) ? m[1].str() : "run";
+  const std::string output_path = "results/" + id + "_convergence_table.txt";
+  { std::ofstream truncate(output_path, std::ios::trunc); }
+  try {
+    for (int i = 0; i < levels; i++) {
+      const auto h_inv = static_cast<unsigned int>(std::round(8 * std::pow(2, i / 2.)));
+      const auto t_inv = static_cast<unsigned int>(std::round(4 * std::pow(2, i)));
+      ms::parabolic::TimeManager manager(h_inv, h_inv, t_inv, input_path, output_path);
+      manager.setup();
+      manager.run();
+    }
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "solve_parabolic: %s\n", e.what());
+    return 2;
+  }
+  return 0;
+}

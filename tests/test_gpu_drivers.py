@@ -1,0 +1,136 @@
+"""GPU tier: the C++ host drivers (Manager / TimeManager with the reference's loops and stop tests,
+micro path on the GPU through the C ABI) against the oracle's drivers, cycle by cycle
+(parity after each of the first K fixed-point cycles / time steps, full history
+where the run converges)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import INPUT, ROOT, OracleBio, OracleElliptic, OracleParabolic, dptr, iptr, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _drivers():
+    import torch  # noqa: F401  (load torch's NCCL before libmsgpu, see dealiiscale_b200/capi.py)
+    from dealiiscale_b200 import capi
+
+    capi.load()
+    lib = C.CDLL(os.path.join(ROOT, "dealiiscale_b200", "_build", "libmsdrivers.so"))
+    for f in ("msdrv_elliptic_create", "msdrv_bio_create", "msdrv_parabolic_create"):
+        getattr(lib, f).restype = C.c_void_p
+    lib.msdrv_last_error.restype = C.c_char_p
+    return lib
+
+
+def _path(prm):
+    return os.path.join(INPUT, prm).encode()
+
+
+@pytest.mark.parametrize("prm,refs,limit", [
+    ("elliptic_linear.prm", (2, 3), -1), ("elliptic_non_linear.prm", (2, 3), -1), ("rot_map_test.prm", (1, 2), -1),
+    ("elliptic_linear.prm", (3, 4), -1),
+    ("map_test.prm", (2, 3), 3), ("arb_map_test.prm", (2, 3), 3), ("lin_map_test.prm", (1, 2), 3),
+])
+def test_solve_elliptic_history(prm, refs, limit):
+    lib = _drivers()
+    o = OracleElliptic(prm, *refs)
+    n_cycles = o.run(limit)
+    h = C.c_void_p(lib.msdrv_elliptic_create(_path(prm), *refs))
+    assert h.value, lib.msdrv_last_error()
+    got = lib.msdrv_elliptic_run(h, limit)
+    assert got == n_cycles, lib.msdrv_last_error()        # identical cycle count
+    N, n = C.c_int(), C.c_int()
+    lib.msdrv_elliptic_sizes(h, C.byref(N), C.byref(n))
+    N, n = N.value, n.value
+    for c in range(n_cycles):
+        ref = o.history(c)
+        errs, macro, contrib = np.zeros(4), np.zeros(N), np.zeros(N)
+        micro, its = np.zeros((N, n)), np.zeros(N, dtype=np.int32)
+        lib.msdrv_elliptic_history(h, c, dptr(errs), dptr(macro), dptr(contrib), dptr(micro), iptr(its))
+        assert rel_l2(macro, ref["macro"]) < 1e-10
+        assert rel_l2(contrib, ref["contribution"]) < 1e-10
+        assert rel_l2(micro, ref["micro"]) < 1e-10
+        np.testing.assert_allclose(errs[[0, 2]], ref["errors"][[0, 2]], rtol=1e-8)     # mL2, ML2
+        np.testing.assert_allclose(errs[[1, 3]], ref["errors"][[1, 3]], rtol=1e-5)     # mH1, MH1 (finite differences)
+    if limit < 0:
+        buf = C.create_string_buffer(1 << 16)
+        lib.msdrv_elliptic_table(h, buf, len(buf))
+        ours = [l.split() for l in buf.value.decode().strip().splitlines()]
+        theirs = [l.split() for l in o.table().strip().splitlines()]
+        assert ours == theirs                                 # printed convergence table, 3 significant digits
+    lib.msdrv_elliptic_destroy(h)
+    o.close()
+
+
+@pytest.mark.parametrize("prm,cells,limit", [
+    ("linear.prm", (4, 16), -1), ("biocase-curved.prm", (3, 8), 6), ("biocase.prm", (4, 8), 5),
+    ("biocase-a.prm", (2, 8), 8),
+])
+def test_solve_biomath_history(prm, cells, limit):
+    lib = _drivers()
+    o = OracleBio(prm, *cells, threads=8)
+    n_cycles = o.run(limit)
+    h = C.c_void_p(lib.msdrv_bio_create(_path(prm), *cells))
+    assert h.value, lib.msdrv_last_error()
+    assert lib.msdrv_bio_run(h, limit) == n_cycles, lib.msdrv_last_error()
+    N, n = C.c_int(), C.c_int()
+    lib.msdrv_bio_sizes(h, C.byref(N), C.byref(n))
+    N, n = N.value, n.value
+    tol = 1e-8 if prm == "biocase-curved.prm" else 1e-9       # warm-started, ill-conditioned systems: see test_gpu_bio
+    for c in range(n_cycles):
+        ref = o.history(c)
+        sc = np.zeros(6)
+        su, sw, cu, cw = (np.zeros(N) for _ in range(4))
+        micro, its = np.zeros((N, n)), np.zeros(N, dtype=np.int32)
+        lib.msdrv_bio_history(h, c, dptr(sc), dptr(su), dptr(sw), dptr(cu), dptr(cw), dptr(micro), iptr(its))
+        assert rel_l2(su, ref["sol_u"]) < tol and rel_l2(sw, ref["sol_w"]) < tol
+        assert rel_l2(cu, ref["cu"]) < tol and rel_l2(cw, ref["cw"]) < tol
+        assert rel_l2(micro, ref["micro"]) < tol
+        if o.has_solution():
+            np.testing.assert_allclose(sc[[0, 2]], [ref["micro_l2"], ref["macro_l2"]], rtol=1e-7)
+        else:
+            np.testing.assert_allclose(sc[4:6], [ref["macro_residual"], ref["micro_residual"]], rtol=1e-4, atol=1e-12)
+    lib.msdrv_bio_destroy(h)
+    o.close()
+
+
+@pytest.mark.parametrize("prm,level", [("linear_time.prm", 0), ("linear_time.prm", 2), ("full_nonlinear.prm", 1)])
+def test_solve_parabolic_history(prm, level):
+    lib = _drivers()
+    h_inv, t_inv = round(8 * 2 ** (level / 2.0)), round(4 * 2 ** level)
+    o = OracleParabolic(prm, h_inv, h_inv, t_inv)
+    steps = o.run()
+    h = C.c_void_p(lib.msdrv_parabolic_create(_path(prm), h_inv, h_inv, t_inv))
+    assert h.value, lib.msdrv_last_error()
+    assert lib.msdrv_parabolic_run(h, -1) == steps, lib.msdrv_last_error()
+    assert lib.msdrv_parabolic_first_step_passes(h) == o.first_step_passes()
+    N, n = C.c_int(), C.c_int()
+    lib.msdrv_parabolic_sizes(h, C.byref(N), C.byref(n))
+    N, n = N.value, n.value
+    for s in range(steps):
+        ref = o.history(s)
+        sc, pi, mass = np.zeros(5), np.zeros(N), np.zeros(N)
+        rho, its = np.zeros((N, n)), np.zeros(N, dtype=np.int32)
+        lib.msdrv_parabolic_history(h, s, dptr(sc), dptr(pi), dptr(mass), dptr(rho), iptr(its))
+        assert sc[0] == ref["time"]
+        assert rel_l2(pi, ref["pi"]) < 1e-10
+        assert rel_l2(rho, ref["rho"]) < 1e-10
+        assert rel_l2(mass, ref["mass"]) < 1e-10
+        np.testing.assert_allclose(sc[1:3], [ref["micro_l2"], ref["macro_l2"]], rtol=1e-7)
+    lib.msdrv_parabolic_destroy(h)
+    o.close()
+
+
+def test_cli_binaries_run_and_write_the_table(tmp_path):
+    exe = os.path.join(ROOT, "dealiiscale_b200", "_build", "solve_biomath")
+    os.makedirs(os.path.join(tmp_path, "results"), exist_ok=True)
+    os.symlink(INPUT, os.path.join(tmp_path, "input"))
+    r = subprocess.run([exe, "input/linear.prm", "1", "3", "0"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Results: 'macro_refinement', 'micro_refinement', 'num_threads', 'wall_time', 'cpu_time'" in r.stdout
+    table = open(os.path.join(tmp_path, "results", "out.txt")).read()
+    assert table.split()[:7] == ["cycle", "cells", "dofs", "mL2", "mH1", "ML2", "MH1"]
