@@ -378,8 +378,19 @@ int msgpu_setup(msgpu_ctx* ctx) {
   if ((rc = build_tables(ctx, 0.0))) return rc;
   ctx->setup_done = 1;
   ctx->assembled = 0;
-  if (prob == MSGPU_PARABOLIC)
+  if (prob == MSGPU_PARABOLIC) {
     if ((rc = parabolic_setup(ctx))) return rc;
+  } else {
+    // The dense equivalent of compute_pullback_objects (micro.cpp:75-94): assemble once, with the
+    // macro values still zero, so that everything the coupling integrals need (det-weighted basis
+    // integrals, boundary stretch weights, boundary loads) exists before the first macro solve —
+    // the reference's first MacroSolver::run() integrates over the micro grids before any
+    // MicroSolver::run() has happened (manager.cpp:53-58).
+    if ((rc = msgpu_assemble(ctx))) return rc;
+    // ... but the solutions themselves start as zero vectors (setup_scatter, micro.cpp:56-72); the
+    // elliptic assembly has just written the Dirichlet values into them
+    CK(cudaMemsetAsync(ctx->d_x, 0, N * n * sizeof(double), ctx->stream));
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   return MSGPU_OK;
 }

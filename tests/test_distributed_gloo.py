@@ -1,0 +1,76 @@
+"""World-size-2 test of the sharded macro <-> micro exchange on CPU (gloo): each rank assembles and
+solves its block of micro systems (product kernel bodies through the CPU harness), the coupling
+integrals are allgathered with the padded-block layout libmsgpu uses over NCCL, rank 0 'solves' the
+macro problem and broadcasts.  The result must equal the single-rank run bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import BIO, INPUT, MESH_SUBDIVIDED, Emul, configure_bio
+from dealiiscale_b200.capi import partition
+from dealiiscale_b200.parallel import MacroSharding
+from dealiiscale_b200.prm import BioData
+
+M = 3  # 3x3 macro points: an odd total, so the last rank's block is padded
+
+
+def _points():
+    g = np.linspace(-1, 1, M)
+    return np.array([(a, b) for b in g for a in g])
+
+
+def _cycle(xy, u, w):
+    e = Emul(BIO, MESH_SUBDIVIDED, 4, 12)
+    configure_bio(e, BioData(os.path.join(INPUT, "biocase-curved.prm")))
+    e.setup(xy)
+    assert e.assemble(u, w) == 0
+    rc, _ = e.solve(1e-12, 10000)
+    assert rc == 0
+    cu, cw = e.coupling()
+    e.close()
+    return cu, cw
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    xy = _points()
+    sh = MacroSharding(len(xy), rank, world)
+    # the macro iterate lives on rank 0 and is broadcast (msgpu_broadcast_macro)
+    u = xy[:, 1] * np.sin(xy[:, 0]) if rank == 0 else np.zeros(len(xy))
+    w = xy[:, 0] * np.cos(xy[:, 1]) if rank == 0 else np.zeros(len(xy))
+    u, w = sh.broadcast(u), sh.broadcast(w)
+    cu, cw = _cycle(sh.local(xy), sh.local(u), sh.local(w))
+    cu_all, cw_all = sh.allgather(cu), sh.allgather(cw)
+    if rank == 0:
+        np.save(out, np.stack([cu_all, cw_all]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_equal_one_rank(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = os.path.join(tmp_path, "gathered.npy")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    xy = _points()
+    cu, cw = _cycle(xy, xy[:, 1] * np.sin(xy[:, 0]), xy[:, 0] * np.cos(xy[:, 1]))
+    assert np.array_equal(got[0], cu) and np.array_equal(got[1], cw)
+
+
+def test_partition_covers_everything_once():
+    for n_total, world in ((9, 2), (4225, 8), (5, 8), (33800, 8)):
+        seen = []
+        for r in range(world):
+            k0, k1 = partition(n_total, world, r)
+            seen += list(range(k0, k1))
+            sh = MacroSharding(n_total, r, world)
+            assert (sh.k0, sh.k1) == (k0, k1) and sh.n_local <= sh.block
+        assert seen == list(range(n_total))

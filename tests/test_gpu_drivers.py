@@ -120,7 +120,8 @@ def test_solve_parabolic_history(prm, level):
         assert rel_l2(pi, ref["pi"]) < 1e-10
         assert rel_l2(rho, ref["rho"]) < 1e-10
         assert rel_l2(mass, ref["mass"]) < 1e-10
-        np.testing.assert_allclose(sc[1:3], [ref["micro_l2"], ref["macro_l2"]], rtol=1e-7)
+        # linear exact solutions are reproduced to rounding (errors ~1e-11): compare those absolutely
+        np.testing.assert_allclose(sc[1:3], [ref["micro_l2"], ref["macro_l2"]], rtol=1e-7, atol=1e-9)
     lib.msdrv_parabolic_destroy(h)
     o.close()
 
