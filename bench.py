@@ -316,7 +316,7 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("k_cg_resident_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("k_cg_strip_bytes_per_launch")
         achieved = cg_bytes / (cg_ms * 1e-3) / 1e9
         value = n_total * n * args.steps / t_dev
         e2e_value = n_total * n * args.steps / t_e2e
@@ -332,7 +332,7 @@ def main():
             "gpu_launches": int(st["launches"]),
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "k_cg_resident<512,9> (batched CG, one CTA per micro system)",
+                "bound": "hbm", "kernel": "k_cg_strip<512,9> (batched CG, one CTA per micro system, shared-memory resident)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": cg_bytes,
