@@ -36,7 +36,7 @@ UNIT = "DoF-solves/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--prm", default="biocase.prm")
@@ -70,7 +70,13 @@ def macro_values(xy):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe), through
+    NVML (same counters as `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*`), every 10 ms."""
+
+    REASONS = {  # nvmlClocksEventReason* bit masks
+        "hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+        "hw_power_brake_slowdown": 0x80,
+    }
 
     def __init__(self, index: int):
         self.index = index
@@ -79,25 +85,54 @@ class ClockSampler:
         self.max_mhz = None
         self._stop = threading.Event()
         self._thread = None
+        self._handle = None
+        try:
+            import pynvml
 
-    def _run(self):
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._handle = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle)
+        for name, bit in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        parts = [p.strip() for p in out.split(",")]
+        if len(parts) >= 6:
+            self.samples.append(float(parts[0]))
+            self.max_mhz = float(parts[1])
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    self.reasons.add(nm)
+
+    def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                parts = [p.strip() for p in out.split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(float(parts[0]))
-                    self.max_mhz = float(parts[1])
-                    for nm, val in zip(names, parts[2:6]):
-                        if val.lower().startswith("active"):
-                            self.reasons.add(nm)
+                if self._handle is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.01 if self._handle is not None else 0.2)
 
     def start(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
@@ -108,7 +143,8 @@ class ClockSampler:
         if self._thread:
             self._thread.join(timeout=6)
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "source": "nvml" if self._handle is not None else "nvidia-smi"}
 
 
 def algorithmic_bytes(n, nnz, iters, n_systems_total):
@@ -202,6 +238,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the micro path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     distributed = world > 1
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL would print its version banner on stdout, ahead of the JSON line
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 

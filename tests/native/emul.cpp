@@ -611,4 +611,14 @@ int emul_mass_integrals(void* h, double* c0) {
   return 0;
 }
 
+int emul_reference_numbering(int mesh_kind, int nc, int* out) {
+  try {
+    const std::vector<int> v = reference_numbering(mesh_kind, nc);
+    std::copy(v.begin(), v.end(), out);
+    return 0;
+  } catch (const std::exception&) {
+    return 1;
+  }
+}
+
 }  // extern "C"

@@ -120,3 +120,42 @@ def test_parabolic_projection_time_steps_mass_and_errors(prm):
     assert np.abs(A - e.matrix(0)).max() <= 1e-13 * np.abs(A).max()
     e.close()
     o.close()
+
+
+@pytest.mark.parametrize("macro_cells,micro_cells", [(1, 1), (1, 2), (2, 5), (1, 7)])
+def test_bio_small_and_odd_meshes(macro_cells, micro_cells):
+    o = OracleBio("biocase-b.prm", macro_cells, micro_cells)
+    e = Emul(BIO, MESH_SUBDIVIDED, micro_cells, 12)
+    configure_bio(e, BioData(os.path.join(INPUT, "biocase-b.prm")))
+    xy = o.grid_locations()
+    e.setup(xy)
+    u, w = 1.0 + xy[:, 0], 0.5 - xy[:, 1]
+    o.micro_run(u, w)
+    assert e.assemble(u, w) == 0
+    e.solve(1e-12, 10000)
+    for k in range(o.N):
+        assert rel_l2(e.solution(k), o.solution(k)) < 1e-10
+    e.close()
+    o.close()
+
+
+def test_dof_numbering_matches_the_oracle():
+    """The product's reference numbering (fe_tables.h) against the oracle's independent one
+    (oracle/fem.h), for both mesh kinds; plus the first-touch pattern itself on a 2x2 mesh."""
+    from helpers import iptr, load_emul, load_oracle
+
+    lib, em = load_oracle(), load_emul()
+    for kind, nc in ((0, 1), (0, 2), (0, 8), (0, 16), (1, 1), (1, 3), (1, 11), (1, 16)):
+        m = nc + 1
+        node_dof = np.zeros(m * m, dtype=np.int32)        # oracle: lexicographic node iy*m+ix -> dof
+        assert lib.orc_numbering(kind, nc, iptr(node_dof)) == 0
+        ref_to_internal = np.zeros(m * m, dtype=np.int32)  # product: dof -> ix*m+iy
+        assert em.emul_reference_numbering(kind, nc, iptr(ref_to_internal)) == 0
+        for dof, r in enumerate(ref_to_internal):
+            ix, iy = divmod(int(r), m)
+            assert node_dof[iy * m + ix] == dof
+    node_dof = np.zeros(9, dtype=np.int32)
+    lib.orc_numbering(1, 2, iptr(node_dof))
+    assert node_dof.tolist() == [0, 1, 4, 2, 3, 5, 6, 7, 8]
+    lib.orc_numbering(0, 2, iptr(node_dof))
+    assert node_dof.tolist() == [0, 1, 4, 2, 3, 5, 6, 7, 8]
