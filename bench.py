@@ -147,6 +147,14 @@ class ClockSampler:
                 "samples": len(self.samples), "source": "nvml" if self._handle is not None else "nvidia-smi"}
 
 
+CG_KERNEL_NAMES = {
+    0: "k_cg_resident (batched CG, one CTA per micro system, matrix resident in shared memory)",
+    1: "k_cg_global (batched CG, matrix streamed from L2/HBM)",
+    2: "k_cg_strip (batched CG, one CTA per micro system, matrix resident in shared memory)",
+    3: "k_cg_strip_tmem (batched CG, one CTA per micro system, matrix resident in tensor memory + shared memory)",
+}
+
+
 def algorithmic_bytes(n, nnz, iters, n_systems_total):
     """SURVEY.md §8d byte model.  Returns (whole step, CG kernel only)."""
     its = np.asarray(iters, dtype=np.float64)
@@ -354,7 +362,7 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("k_cg_strip_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("cg_bytes_per_launch")
         achieved = cg_bytes / (cg_ms * 1e-3) / 1e9
         value = n_total * n * args.steps / t_dev
         e2e_value = n_total * n * args.steps / t_e2e
@@ -370,11 +378,11 @@ def main():
             "gpu_launches": int(st["launches"]),
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "k_cg_strip<512,9> (batched CG, one CTA per micro system, shared-memory resident)",
+                "bound": "hbm", "kernel": CG_KERNEL_NAMES.get(int(st["cg_variant"]), "batched CG"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": cg_bytes,
-                "note": "the CG keeps each system in shared memory: the matrix is read from HBM once per solve, "
+                "note": "the CG keeps each system on chip (tensor memory, shared memory, registers): the matrix is read from HBM once per solve, "
                         "not once per iteration, so algorithmic bytes / time can exceed the HBM peak (on-chip resident)",
                 "step_algorithmic_bytes": step_bytes,
                 "step_achieved_GBps": step_bytes / (dev_ms_step * 1e-3) / 1e9,

@@ -19,6 +19,7 @@
 // alpha = gh/(d.h); x += alpha d; g += alpha h; res = |g|; stop if res <= tol;
 // beta = res^2/gh; d = beta d - g }.  Dot products use a fixed shuffle tree + fixed order over
 // warps, so results are bit-reproducible from run to run and independent of the SM.
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 
@@ -46,6 +47,52 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   __syncthreads();
   double t = (lane < NW) ? red[lane] : 0.0;
   return warp_sum(t);
+}
+
+// Same contract, shorter dependency chain for small warp counts: every thread reads all NW warp
+// sums (broadcast loads) and adds them in one fixed binary tree instead of a second shuffle tree.
+template <int BT>
+__device__ __forceinline__ double block_sum_tree(double v, double* red) {
+  constexpr int NW = BT / 32;
+  static_assert(NW >= 2 && NW <= 16 && NW % 2 == 0, "warp count");
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double t[16];
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    if (i < NW) {
+      const double2 p = *reinterpret_cast<const double2*>(red + i);
+      t[i] = p.x;
+      t[i + 1] = p.y;
+    } else {
+      t[i] = 0.0;
+      t[i + 1] = 0.0;
+    }
+  }
+#pragma unroll
+  for (int w2 = 1; w2 < 16; w2 *= 2)
+#pragma unroll
+    for (int i = 0; i + w2 < 16; i += 2 * w2)
+      if (i + w2 < NW) t[i] += t[i + w2];
+  return t[0];
+}
+
+// Dot-product partial of a strip: NACC independent accumulators (fixed assignment j % NACC, fixed
+// combination order) so that a long strip is not one serial chain of K dependent DFMAs.
+template <int K, int NACC, class F>
+__device__ __forceinline__ double strip_dot(F&& term) {
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) acc[j % NACC] += term(j);
+#pragma unroll
+  for (int w2 = 1; w2 < NACC; w2 *= 2)
+#pragma unroll
+    for (int i = 0; i + w2 < NACC; i += 2 * w2) acc[i] += acc[i + w2];
+  return acc[0];
 }
 
 // -------------------------------------------------------------------------------------------
@@ -415,6 +462,272 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip(CgArgs a) {
   }
 }
 
+
+// -------------------------------------------------------------------------------------------
+// Strip CG with the matrix in TENSOR MEMORY (TMEM).
+//
+// The strip kernel above is limited by the shared-memory pipe, and 8 of its ~11 loads per row
+// are matrix entries.  Seven of them are needed by the thread that owns row r and by nobody else:
+// M0[r], M2[r], M3[r], M4[r] and the transposed M2[r-(m-1)], M3[r-m], M4[r-(m+1)] — a lane-private
+// pattern, which is exactly what TMEM offers: 128 lanes x 512 32-bit columns per SM behind its own
+// datapath (tcgen05.ld / tcgen05.st), unused otherwise in this FP64 kernel.  Warp w may touch lanes
+// 32*(w%4)..+31; the BT/128 warps of a lane quadrant split the 512 columns, so a thread has
+// 64 (BT = 512) or 128 (BT = 256) doubles of TMEM.  Row j of the strip keeps its 7 entries in
+// columns 14j..14j+13 and fetches them with ONE tcgen05.ld.32x32b.x16 per row per iteration (the
+// two surplus columns belong to the next row / are never used), software-pipelined one row ahead.
+// Shared memory then only serves M1 and the search direction (~3.7 instead of ~11.8 loads per
+// row); M2..M4 are staged there once per system for the transposed pick-up.
+// Rows past n are handled without branches: their matrix entries are exact zeros and dead threads
+// work on the zero guard behind d, so the compiler is free to interleave the rows of a strip.
+// Every lane of every warp executes the (sync.aligned) tcgen05 instructions.
+struct TmemRow {
+  uint32_t r[16];
+};
+__device__ __forceinline__ void tmem_store_row(uint32_t taddr, const double (&v)[7]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};\n"
+      "tcgen05.wait::st.sync.aligned;\n" ::"r"(taddr),
+      "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])),
+      "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])),
+      "r"(__double2loint(v[4])), "r"(__double2hiint(v[4])), "r"(__double2loint(v[5])), "r"(__double2hiint(v[5])),
+      "r"(__double2loint(v[6])), "r"(__double2hiint(v[6])), "r"(0), "r"(0));
+}
+// Asynchronous TMEM load of one row (16 columns) and the matching wait.  TMEM is not aliased by any
+// pointer, so neither needs a "memory" clobber (which would also fence the shared-memory loads of
+// neighbouring rows); the wait takes the destination registers as in/out operands so that no use of
+// them can be scheduled before it.
+__device__ __forceinline__ void tmem_issue_row(uint32_t taddr, TmemRow& q) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];\n"
+      : "=r"(q.r[0]), "=r"(q.r[1]), "=r"(q.r[2]), "=r"(q.r[3]), "=r"(q.r[4]), "=r"(q.r[5]), "=r"(q.r[6]), "=r"(q.r[7]),
+        "=r"(q.r[8]), "=r"(q.r[9]), "=r"(q.r[10]), "=r"(q.r[11]), "=r"(q.r[12]), "=r"(q.r[13]), "=r"(q.r[14]),
+        "=r"(q.r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_row(TmemRow& q) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(q.r[0]), "+r"(q.r[1]), "+r"(q.r[2]), "+r"(q.r[3]), "+r"(q.r[4]), "+r"(q.r[5]), "+r"(q.r[6]),
+                 "+r"(q.r[7]), "+r"(q.r[8]), "+r"(q.r[9]), "+r"(q.r[10]), "+r"(q.r[11]), "+r"(q.r[12]), "+r"(q.r[13]));
+}
+__device__ __forceinline__ double tmem_get(const TmemRow& q, int i) { return __hiloint2double(q.r[2 * i + 1], q.r[2 * i]); }
+
+__host__ __device__ constexpr int tmem_pad(int m, int K) { return (m + 3 + K) & ~1; }
+
+template <int BT, int K, bool JACOBI>
+__global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
+  constexpr int CW = (512 / (BT / 128)) & ~1;  // TMEM columns per warp
+  constexpr int NACC = K >= 12 ? 4 : 1;        // K = 9 stays bit-identical to k_cg_strip
+  static_assert(BT % 128 == 0 && 14 * K + 2 <= CW, "strip must fit the TMEM columns of a thread");
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int s_k;
+  __shared__ uint32_t s_tmem;
+  const int n = a.md.n, m = a.md.m, ld = a.md.ld;
+  const int pad = tmem_pad(m, K);  // >= m + 1 + K: dead rows n..n+K-1 stay inside the guards
+  const int ms = pad + ld;
+  // shared memory: M1..M4 (4 diagonals) + d with halos + reduction scratch
+  double* const mat = sm;
+  double* const dv = sm + 4 * ms + pad;
+  double* const red = sm + ((4 * ms + n + 2 * pad + 1) & ~1);  // 16-byte aligned
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int r0 = tid * K;
+  const int rc0 = r0 < n ? r0 : n;                      // dead threads work on the zero guard
+  const int nlive = r0 < n ? (n - r0 < K ? n - r0 : K) : 0;  // rows of this strip inside the system
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(
+        static_cast<uint32_t>(__cvta_generic_to_shared(&s_tmem))));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  for (int i = tid; i < 4 * ms; i += BT)
+    if ((i % ms) < pad || (i % ms) >= pad + n) mat[i] = 0.0;
+  for (int i = tid; i < pad; i += BT) {
+    dv[-pad + i] = 0.0;
+    dv[n + i] = 0.0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n");
+  // lane quadrant of this warp in bits 31:16, column block of this warp in bits 15:0
+  const uint32_t tbase =
+      s_tmem + ((static_cast<uint32_t>(warp & 3) * 32u) << 16) + static_cast<uint32_t>(warp >> 2) * static_cast<uint32_t>(CW);
+
+  const double* const M1 = mat + pad;
+  const double* const M2 = M1 + ms;
+  const double* const M3 = M2 + ms;
+  const double* const M4 = M3 + ms;
+
+  // h = A d for the K rows of this thread; dl = own entries of d (registers), dv = all of d (shared)
+  auto spmv_strip = [&](const double (&dl)[K], double (&hh)[K]) {
+    // sliding windows over the right (r+m-1, r+m, r+m+1) and left (r-m-1, r-m, r-m+1) columns
+    double ra = dv[rc0 + m - 1], rb = dv[rc0 + m];
+    double la = dv[rc0 - m - 1], lb = dv[rc0 - m];
+    double below = dv[rc0 - 1];
+    double m1_prev = M1[rc0 - 1];
+    TmemRow q[2];  // double buffer; the loop is fully unrolled, so q[j & 1] are plain registers
+    tmem_issue_row(tbase, q[0]);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int r = rc0 + j;
+      TmemRow& cur = q[j & 1];
+      tmem_wait_row(cur);
+      if (j + 1 < K) tmem_issue_row(tbase + 14u * (j + 1), q[(j + 1) & 1]);  // one row ahead
+      const double rc = dv[r + m + 1], lc = dv[r - m + 1];
+      const double m1 = M1[r];
+      const double above = (j + 1 < K) ? dl[j + 1] : dv[r + 1];
+      double s = tmem_get(cur, 0) * dl[j];
+      s += m1 * above;
+      s += m1_prev * below;
+      s += tmem_get(cur, 1) * ra;
+      s += tmem_get(cur, 4) * lc;
+      s += tmem_get(cur, 2) * rb;
+      s += tmem_get(cur, 5) * lb;
+      s += tmem_get(cur, 3) * rc;
+      s += tmem_get(cur, 6) * la;
+      hh[j] = s;
+      ra = rb; rb = rc;
+      la = lb; lb = lc;
+      below = dl[j];
+      m1_prev = m1;
+    }
+  };
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_k = atomicAdd(a.work_counter, 1);
+    __syncthreads();
+    const int k = s_k;
+    if (k >= a.N) break;
+
+    const double* dg = a.diag + static_cast<size_t>(k) * a.diag_stride;
+    // stage M1..M4 in shared memory; M0 goes through the d buffer on its way to TMEM
+    for (int d = 1; d < NDIAG; ++d) {
+      const double* src = dg + static_cast<size_t>(d) * ld;
+      double* dst = mat + (d - 1) * ms + pad;
+      for (int r = tid; r < n; r += BT) dst[r] = __ldg(src + r);
+    }
+    for (int r = tid; r < n; r += BT) dv[r] = __ldg(dg + r);
+    __syncthreads();
+    double diag_own[JACOBI ? K : 1];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int r = rc0 + j;
+      const bool in = j < nlive;
+      double v[7];
+      v[0] = in ? dv[r] : 0.0;
+      v[1] = in ? M2[r] : 0.0;
+      v[2] = in ? M3[r] : 0.0;
+      v[3] = in ? M4[r] : 0.0;
+      v[4] = in ? M2[r - (m - 1)] : 0.0;
+      v[5] = in ? M3[r - m] : 0.0;
+      v[6] = in ? M4[r - (m + 1)] : 0.0;
+      if (JACOBI) diag_own[j] = in ? v[0] : 1.0;
+      tmem_store_row(tbase + 14u * j, v);  // ascending j: the two surplus columns are rewritten by row j+1
+    }
+    __syncthreads();  // everybody has picked up M0 before d is overwritten
+
+    double xx[K], gg[K], dl[K], hh[K];
+    const double* bk = a.b + static_cast<size_t>(k) * n;
+    double* xk = a.x + static_cast<size_t>(k) * n;
+    for (int r = tid; r < n; r += BT) dv[r] = xk[r];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      xx[j] = (j < nlive) ? dv[r0 + j] : 0.0;
+      dl[j] = xx[j];
+    }
+    spmv_strip(dl, hh);
+    double part = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      gg[j] = (j < nlive) ? (hh[j] - bk[r0 + j]) : 0.0;
+      part += gg[j] * gg[j];
+    }
+    double res = sqrt(block_sum_tree<BT>(part, red));
+    int it = 0;
+    bool ok = res <= a.tol;
+    double gh = 0.0;
+    if (!ok) {
+      __syncthreads();
+      if (JACOBI) {
+        part = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const double z = gg[j] / diag_own[j];
+          dl[j] = -z;
+          part += gg[j] * z;
+          if (j < nlive) dv[r0 + j] = dl[j];
+        }
+        gh = block_sum_tree<BT>(part, red + 32);
+      } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          dl[j] = -gg[j];
+          if (j < nlive) dv[r0 + j] = dl[j];
+        }
+        gh = res * res;
+      }
+      for (;;) {
+        ++it;
+        __syncthreads();
+        spmv_strip(dl, hh);
+        part = strip_dot<K, NACC>([&](int j) { return dl[j] * hh[j]; });
+        const double alpha = gh / block_sum_tree<BT>(part, red);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          xx[j] += alpha * dl[j];
+          gg[j] += alpha * hh[j];
+        }
+        part = strip_dot<K, NACC>([&](int j) { return gg[j] * gg[j]; });
+        res = sqrt(block_sum_tree<BT>(part, red + 32));
+        if (res <= a.tol) {
+          ok = true;
+          break;
+        }
+        if (it >= a.max_it || res != res) break;
+        double beta = gh;
+        if (JACOBI) {
+          part = 0.0;
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            hh[j] = gg[j] / diag_own[j];
+            part += gg[j] * hh[j];
+          }
+          gh = block_sum_tree<BT>(part, red + 64);
+          beta = gh / beta;
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            dl[j] = beta * dl[j] - hh[j];
+            if (j < nlive) dv[r0 + j] = dl[j];
+          }
+        } else {
+          gh = res * res;
+          beta = gh / beta;
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            dl[j] = beta * dl[j] - gg[j];
+            if (j < nlive) dv[r0 + j] = dl[j];
+          }
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+      if (j < nlive) dv[r0 + j] = xx[j];
+    __syncthreads();
+    for (int r = tid; r < n; r += BT) xk[r] = dv[r];
+    if (tid == 0) {
+      if (a.iters) a.iters[k] = it;
+      if (a.res) a.res[k] = res;
+      if (!ok) atomicExch(a.fail_flag, 1);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(s_tmem));
+}
+
 // -------------------------------------------------------------------------------------------
 // Global-memory CG for systems that do not fit in one SM's shared memory (m > 67): the matrix is
 // streamed from L2/HBM every iteration, work vectors live in a per-CTA workspace.  Same
@@ -589,6 +902,22 @@ int launch_strip(cudaStream_t s, const CgArgs& a, int num_sms) {
   return 1;
 }
 
+size_t tmem_smem_bytes(const MeshDims& md, int K) {
+  const int pad = tmem_pad(md.m, K);
+  return (static_cast<size_t>(4) * (pad + md.ld) + md.n + 2 * pad + 98) * sizeof(double);
+}
+
+template <int BT, int K>
+int launch_strip_tmem(cudaStream_t s, const CgArgs& a, int num_sms) {
+  const size_t smem = tmem_smem_bytes(a.md, K);
+  auto kern = a.precond == 1 ? k_cg_strip_tmem<BT, K, true> : k_cg_strip_tmem<BT, K, false>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  long long grid = num_sms;  // one CTA per SM: each allocates all 512 TMEM columns
+  if (grid > a.N) grid = a.N;
+  kern<<<static_cast<int>(grid), BT, smem, s>>>(a);
+  return 1;
+}
+
 template <int BT, int RPT>
 int launch_resident(cudaStream_t s, const CgArgs& a, int num_sms) {
   const size_t smem = resident_smem_bytes(a.md);
@@ -619,6 +948,13 @@ int launch_cg(cudaStream_t s, const CgArgs& a, int num_sms, int* variant) {
     if (variant) *variant = 0;
     const char* wide = std::getenv("MSGPU_CG_WIDE");  // "1": 1024 threads x 5 rows instead of 512 x 9
     const char* strided = std::getenv("MSGPU_CG_STRIDED");  // "1": strided row ownership (A/B measurements)
+    const char* tmem = std::getenv("MSGPU_CG_TMEM");  // "0": off, "5": force the 512 x 9 shape
+    // default for the large resident sizes: matrix in tensor memory ("0" = plain strip kernel, A/B)
+    if (!(tmem && tmem[0] == '0') && !(strided && strided[0] == '1') && n > 2560) {
+      if (variant) *variant = 3;
+      if (n <= 256 * 17 && !(tmem && tmem[0] == '5')) return launch_strip_tmem<256, 17>(s, a, num_sms);
+      if (n <= 512 * 9) return launch_strip_tmem<512, 9>(s, a, num_sms);
+    }
     if (!(strided && strided[0] == '1')) {
       if (variant) *variant = 2;
       if (n <= 32) return launch_strip<32, 1>(s, a, num_sms);

@@ -172,7 +172,8 @@ typedef struct {
   double ms_coupling;  /* coupling integrals (+ collectives)           */
   long long launches;  /* kernels launched by this context so far      */
   long long cg_iterations_total; /* sum over systems of the last solve */
-  int cg_variant;      /* 0 = shared-memory resident (strided rows), 1 = global-memory, 2 = resident (row strips) */
+  int cg_variant;      /* 0 = shared-memory resident (strided rows), 1 = global-memory, 2 = resident (row strips),
+                          3 = row strips with the matrix in tensor memory */
 } msgpu_stats;
 int msgpu_enable_timing(msgpu_ctx* ctx, int on);
 int msgpu_get_stats(msgpu_ctx* ctx, msgpu_stats* out, int reset);
