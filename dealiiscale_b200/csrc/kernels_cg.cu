@@ -576,16 +576,30 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
       const double rc = dv[r + m + 1], lc = dv[r - m + 1];
       const double m1 = M1[r];
       const double above = (j + 1 < K) ? dl[j + 1] : dv[r + 1];
-      double s = tmem_get(cur, 0) * dl[j];
-      s += m1 * above;
-      s += m1_prev * below;
-      s += tmem_get(cur, 1) * ra;
-      s += tmem_get(cur, 4) * lc;
-      s += tmem_get(cur, 2) * rb;
-      s += tmem_get(cur, 5) * lb;
-      s += tmem_get(cur, 3) * rc;
-      s += tmem_get(cur, 6) * la;
-      hh[j] = s;
+      if (NACC == 1) {
+        double s = tmem_get(cur, 0) * dl[j];
+        s += m1 * above;
+        s += m1_prev * below;
+        s += tmem_get(cur, 1) * ra;
+        s += tmem_get(cur, 4) * lc;
+        s += tmem_get(cur, 2) * rb;
+        s += tmem_get(cur, 5) * lb;
+        s += tmem_get(cur, 3) * rc;
+        s += tmem_get(cur, 6) * la;
+        hh[j] = s;
+      } else {
+        // two shorter dependency chains per row (same terms, fixed order)
+        double s = tmem_get(cur, 0) * dl[j];
+        double t = tmem_get(cur, 1) * ra;
+        s += m1 * above;
+        t += tmem_get(cur, 4) * lc;
+        s += m1_prev * below;
+        t += tmem_get(cur, 2) * rb;
+        s += tmem_get(cur, 5) * lb;
+        t += tmem_get(cur, 3) * rc;
+        s += tmem_get(cur, 6) * la;
+        hh[j] = s + t;
+      }
       ra = rb; rb = rc;
       la = lb; lb = lc;
       below = dl[j];
