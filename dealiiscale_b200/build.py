@@ -16,7 +16,7 @@ BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(BUILD, "libmsgpu.so")
 
 CUDA_SOURCES = ["msgpu.cu", "kernels_assemble.cu", "kernels_cg.cu", "kernels_extra.cu", "comm.cu"]
-HOST_SOURCES = ["expr_compile.cpp", "problem_programs.cpp"]
+HOST_SOURCES = ["expr_compile.cpp", "problem_programs.cpp", "jit.cpp", "jit_codegen.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -25,7 +25,7 @@ EXPORTED = [
     "msgpu_coupling", "msgpu_errors", "msgpu_residuals", "msgpu_get_solutions", "msgpu_set_solutions",
     "msgpu_zero_solutions", "msgpu_get_rhs", "msgpu_get_dof_permutation", "msgpu_get_dof_points", "msgpu_get_matrix_dense",
     "msgpu_comm_unique_id", "msgpu_partition", "msgpu_comm_init", "msgpu_broadcast_macro", "msgpu_enable_timing",
-    "msgpu_get_stats",
+    "msgpu_get_stats", "msgpu_jit_log",
 ]
 
 
@@ -37,7 +37,7 @@ class Desc(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ms_tables", C.c_double), ("ms_moments", C.c_double), ("ms_gather", C.c_double),
                 ("ms_cg", C.c_double), ("ms_coupling", C.c_double), ("launches", C.c_longlong),
-                ("cg_iterations_total", C.c_longlong), ("cg_variant", C.c_int)]
+                ("cg_iterations_total", C.c_longlong), ("cg_variant", C.c_int), ("jit_kernels", C.c_int)]
 
 
 class MsgpuError(RuntimeError):
@@ -68,6 +68,8 @@ def load():
     lib.msgpu_destroy.restype = None
     lib.msgpu_last_error.argtypes = [vp]
     lib.msgpu_last_error.restype = C.c_char_p
+    lib.msgpu_jit_log.argtypes = [vp]
+    lib.msgpu_jit_log.restype = C.c_char_p
     lib.msgpu_set_stream.argtypes = [vp, vp]
     lib.msgpu_synchronize.argtypes = [vp]
     lib.msgpu_set_grid_locations.argtypes = [vp, dp, C.c_int]

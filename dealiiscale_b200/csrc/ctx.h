@@ -11,6 +11,7 @@
 #include "expr_compile.h"
 #include "problem_programs.h"
 #include "kernels.h"
+#include "jit.h"
 
 namespace msgpu {
 
@@ -41,6 +42,11 @@ struct msgpu_ctx {
 
   // compiled expressions
   msgpu::ProblemPrograms pp;
+
+  // run-time specialised kernels (jit.h); jit_log keeps why a specialisation was not possible
+  msgpu::JitKernel jit_moments;
+  int jit_kernels = 0;
+  std::string jit_log;
 
   // mesh
   msgpu::MeshDims md{};

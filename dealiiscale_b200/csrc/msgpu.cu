@@ -306,6 +306,32 @@ int msgpu_setup(msgpu_ctx* ctx) {
     for (int i = 0; i < QTAB_STRIDE; ++i) qsum[i] += qtab[static_cast<size_t>(q) * QTAB_STRIDE + i];
   if (upload_constant_tables(md.q, qtab.data(), qsum.data()))
     return fail(ctx, MSGPU_ERR_CUDA, "cannot upload the quadrature tables to constant memory");
+  // Specialise the cell-moment kernel for this problem's expressions (elliptic and bio assemble
+  // every cycle).  Any failure leaves the interpreter kernels in charge and is kept in jit_log.
+  ctx->jit_kernels = 0;
+  ctx->jit_log.clear();
+  {
+    const char* jit_env = std::getenv("MSGPU_JIT");
+    if (ctx->desc.problem != MSGPU_PARABOLIC && !(jit_env && jit_env[0] == '0')) {
+      const ProgramSet& ps = ctx->pp.ps;
+      MomentPrograms mp;
+      mp.full = &ps.point_program(ctx->pp.prog_vol);
+      mp.F = ctx->pp.prog_vol_F >= 0 ? &ps.point_program(ctx->pp.prog_vol_F) : mp.full;
+      mp.G = &ps.point_program(ctx->pp.prog_vol_G);
+      mp.has_map = ctx->pp.has_map;
+      mp.jac_depends_on_y = ctx->pp.jac_depends_on_y;
+      bool unrolled = false;
+      const std::string src = cell_moments_source(mp, md.q, qtab.data(), qsum.data(), &unrolled);
+      if (src.empty()) {
+        ctx->jit_log = "the volume program uses an instruction the code generator does not lower";
+      } else if (jit_compile(src, "k_cell_moments_jit", &ctx->jit_moments, &ctx->jit_log) == 0) {
+        ctx->jit_moments.unrolled_rows = unrolled;
+        ctx->jit_kernels = 1;
+      }
+    } else if (jit_env && jit_env[0] == '0') {
+      ctx->jit_log = "disabled by MSGPU_JIT=0";
+    }
+  }
   std::vector<double> c0(md.P), c1(md.P);
   for (int p = 0; p < md.nc * md.q; ++p) {
     const int cx = p / md.q, qx = p % md.q;
@@ -430,9 +456,15 @@ int msgpu_assemble(msgpu_ctx* ctx) {
       mp.G = &ps.point_program(ctx->pp.prog_vol_G);
       mp.has_map = ctx->pp.has_map;
       mp.jac_depends_on_y = ctx->pp.jac_depends_on_y;
-      ctx->launches += launch_cell_moments(ctx->stream, mp, md, tb, ctx->d_qtab,
-                                           ctx->d_qtab + static_cast<size_t>(md.q) * md.q * QTAB_STRIDE, k0, nk, d2,
-                                           ctx->d_cell, ctx->d_flags + FLAG_JACOBIAN);
+      int launched = -1;
+      if (ctx->jit_kernels)
+        launched = launch_cell_moments_jit(ctx->stream, ctx->jit_moments, md, tb, k0, nk, d2, ctx->d_cell,
+                                           ctx->d_flags + FLAG_JACOBIAN);
+      if (launched < 0)
+        launched = launch_cell_moments(ctx->stream, mp, md, tb, ctx->d_qtab,
+                                       ctx->d_qtab + static_cast<size_t>(md.q) * md.q * QTAB_STRIDE, k0, nk, d2,
+                                       ctx->d_cell, ctx->d_flags + FLAG_JACOBIAN);
+      ctx->launches += launched;
       if (prob == MSGPU_BIO)
         for (int s = 0; s < 4; ++s)
           ctx->launches += launch_face_moments(ctx->stream, ps.point_program(ctx->pp.prog_face[s]), s, md, tb, ctx->d_q1pt,
@@ -681,6 +713,8 @@ int msgpu_enable_timing(msgpu_ctx* ctx, int on) {
   return MSGPU_OK;
 }
 
+const char* msgpu_jit_log(const msgpu_ctx* ctx) { return ctx ? ctx->jit_log.c_str() : "null context"; }
+
 int msgpu_get_stats(msgpu_ctx* ctx, msgpu_stats* out, int reset) {
   if (!ctx || !out) return MSGPU_ERR_INVALID;
   CK(cudaStreamSynchronize(ctx->stream));
@@ -693,6 +727,7 @@ int msgpu_get_stats(msgpu_ctx* ctx, msgpu_stats* out, int reset) {
   out->launches = ctx->launches;
   out->cg_iterations_total = ctx->cg_iterations_total;
   out->cg_variant = ctx->cg_variant;
+  out->jit_kernels = ctx->jit_kernels;
   if (reset) {
     for (double& v : ctx->phase_ms) v = 0;
     ctx->launches = 0;

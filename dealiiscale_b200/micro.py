@@ -262,6 +262,10 @@ class MicroSolver:
         self._check(self.lib.msgpu_get_stats(self.h, C.byref(s), int(reset)))
         return {f: getattr(s, f) for f, _ in capi.Stats._fields_}
 
+    def jit_log(self) -> str:
+        """Why the run-time specialised kernels are not in use ('' when they are)."""
+        return self.lib.msgpu_jit_log(self.h).decode()
+
 
 def unique_id() -> bytes:
     buf = C.create_string_buffer(128)

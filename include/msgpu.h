@@ -174,8 +174,12 @@ typedef struct {
   long long cg_iterations_total; /* sum over systems of the last solve */
   int cg_variant;      /* 0 = shared-memory resident (strided rows), 1 = global-memory, 2 = resident (row strips),
                           3 = row strips with the matrix in tensor memory */
+  int jit_kernels;     /* assembly kernels specialised at run time (NVRTC) for this problem; 0 = the
+                          bytecode interpreter runs at every quadrature point (MSGPU_JIT=0, or no NVRTC) */
 } msgpu_stats;
 int msgpu_enable_timing(msgpu_ctx* ctx, int on);
+/* Why msgpu_stats.jit_kernels is 0 (empty string when the specialised kernels are in use). */
+const char* msgpu_jit_log(const msgpu_ctx* ctx);
 int msgpu_get_stats(msgpu_ctx* ctx, msgpu_stats* out, int reset);
 
 #ifdef __cplusplus

@@ -14,6 +14,7 @@
 #include "../../dealiiscale_b200/csrc/assemble_bodies.cuh"
 #include "../../dealiiscale_b200/csrc/extra_bodies.cuh"
 #include "../../dealiiscale_b200/csrc/fe_tables.h"
+#include "../../dealiiscale_b200/csrc/jit.h"
 #include "../../dealiiscale_b200/csrc/problem_programs.h"
 
 using namespace msgpu;
@@ -91,6 +92,53 @@ int emul_moment_mode(void* h) {
   Emul* e = static_cast<Emul*>(h);
   return !e->pp.has_map ? MODE_NO_MAP : (e->pp.jac_depends_on_y ? MODE_GENERAL : MODE_CONST_F);
 }
+// Text of the run-time specialised cell-moment kernel for this problem (what the product hands to
+// NVRTC).  Returns the length needed (including the terminating zero); 0 = not expressible.
+int emul_jit_source(void* h, char* buf, int len) {
+  Emul* e = static_cast<Emul*>(h);
+  const ProgramSet& ps = e->pp.ps;
+  MomentPrograms mp;
+  mp.full = &ps.point_program(e->pp.prog_vol);
+  mp.F = e->pp.prog_vol_F >= 0 ? &ps.point_program(e->pp.prog_vol_F) : mp.full;
+  mp.G = &ps.point_program(e->pp.prog_vol_G);
+  mp.has_map = e->pp.has_map;
+  mp.jac_depends_on_y = e->pp.jac_depends_on_y;
+  bool unrolled = false;
+  const std::string src = cell_moments_source(mp, e->md.q, e->qtab.data(), e->qsum.data(), &unrolled);
+  if (src.empty()) return 0;
+  if (buf && len > 0) {
+    std::strncpy(buf, src.c_str(), len - 1);
+    buf[len - 1] = 0;
+  }
+  return static_cast<int>(src.size()) + 1;
+}
+// Raw table pointers for running that text on the host (tests only).
+int emul_table_pointers(void* h, const double** slots, const double** T0, const double** T1, int* dims) {
+  Emul* e = static_cast<Emul*>(h);
+  const Tables tb = e->tables();
+  *slots = tb.slots;
+  *T0 = tb.T0;
+  *T1 = tb.T1;
+  dims[0] = tb.n_slots;
+  dims[1] = tb.n0;
+  dims[2] = tb.n1;
+  dims[3] = e->md.nc;
+  dims[4] = e->md.m;
+  dims[5] = e->md.n;
+  dims[6] = e->md.ld;
+  dims[7] = e->md.ncells;
+  dims[8] = e->md.q;
+  dims[9] = e->md.P;
+  return 0;
+}
+double emul_mesh_h(void* h) { return static_cast<Emul*>(h)->md.h; }
+int emul_get_cell_scratch(void* h, double* out, long long count) {
+  Emul* e = static_cast<Emul*>(h);
+  if (count > static_cast<long long>(e->cell.size())) count = static_cast<long long>(e->cell.size());
+  std::memcpy(out, e->cell.data(), sizeof(double) * count);
+  return static_cast<int>(count);
+}
+
 int emul_set_scalars(void* h, const double* v, int n) {
   Emul* e = static_cast<Emul*>(h);
   for (int i = 0; i < n; ++i) e->scalars[i] = v[i];
