@@ -49,7 +49,7 @@ def _assembled(problem, prm, cells, xy, u, w, jit):
 CASES = [
     ("bio", "biocase.prm", 8),            # const-F mode, identity map
     ("bio", "biocase-b.prm", 5),          # const-F mode, affine map, odd cell count
-    ("bio", "biocase-curved.prm", 8),     # general mode
+    ("bio", "biocase-curved.prm", 8),     # const-F mode, F depends on the macro position
     ("elliptic", "elliptic_linear.prm", 8),
     ("elliptic", "elliptic_non_linear.prm", 8),
     ("elliptic", "rot_map_test.prm", 4),

@@ -1,0 +1,148 @@
+"""CPU tier: the code generator behind the run-time specialised cell-moment kernel (csrc/jit_codegen.cpp).
+
+1. The generated CUDA C is compiled as HOST C++ behind a small shim (g++, no FMA contraction) and run
+   cell by cell; its output must equal the interpreter body's (tests/native harness) bit for bit.
+2. NVRTC (which needs no GPU) must accept the same text for sm_100a.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import INPUT, Emul, configure_bio, configure_elliptic, dptr
+
+SHIM = r"""
+#include <cmath>
+#include <cstring>
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __constant__ static const
+#define __launch_bounds__(x)
+struct Idx3 { unsigned x, y, z; };
+static Idx3 blockIdx, threadIdx;
+static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+"""
+
+DRIVER = r"""
+extern "C" void host_run(const int* d, double h, const double* slots, const double* T0, const double* T1, int nk,
+                         double scale, double* cell, int* flag) {
+  MeshDims md{d[3], d[4], d[5], d[6], d[7], d[8], d[9], h};
+  Tables tb{slots, T0, T1, d[0], d[1], d[2]};
+  const long long work = static_cast<long long>(nk) * md.ncells;
+  for (long long t = 0; t < work; ++t) {
+    blockIdx.x = static_cast<unsigned>(t / 128);
+    threadIdx.x = static_cast<unsigned>(t % 128);
+    k_cell_moments_jit(md, tb, 0, nk, scale, cell, flag);
+  }
+}
+"""
+
+
+def _emul(problem, prm, nc, q):
+    from dealiiscale_b200.prm import BioData, EllipticData
+
+    if problem == "bio":
+        e = Emul(1, 1, nc, q)
+        configure_bio(e, BioData(os.path.join(INPUT, prm)))
+    else:
+        e = Emul(0, 0, nc, q)
+        configure_elliptic(e, EllipticData(os.path.join(INPUT, prm)))
+    xy = np.array([[-0.5, 0.25], [0.3, 0.7], [0.9, -0.9]])
+    e.setup(xy)
+    return e, xy
+
+
+def _source(e):
+    e.lib.emul_jit_source.restype = C.c_int
+    e.lib.emul_jit_source.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    n = e.lib.emul_jit_source(e.h, None, 0)
+    assert n > 0, "the volume program could not be lowered"
+    buf = C.create_string_buffer(n)
+    e.lib.emul_jit_source(e.h, buf, n)
+    return buf.value.decode()
+
+
+CASES = [
+    ("bio", "biocase.prm", 3, 12, 1),             # const-F
+    ("bio", "biocase-curved.prm", 3, 12, 1),      # const-F: the map bends with the macro position only
+    ("elliptic", "elliptic_non_linear.prm", 2, 12, 0),
+    ("elliptic", "rot_map_test.prm", 4, 12, 1),
+    ("elliptic", "elliptic_linear.prm", 4, 3, 1),  # another quadrature
+]
+
+
+@pytest.mark.parametrize("problem,prm,nc,q,mode", CASES)
+def test_generated_kernel_equals_interpreter_on_the_host(problem, prm, nc, q, mode, tmp_path):
+    e, xy = _emul(problem, prm, nc, q)
+    assert e.moment_mode() == mode
+    src = _source(e)
+    cpp = tmp_path / "k.cpp"
+    cpp.write_text(SHIM + src + DRIVER)
+    so = tmp_path / "k.so"
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                           "-Wno-unknown-pragmas", "-o", str(so), str(cpp)])
+    lib = C.CDLL(str(so))
+
+    # interpreter body (what k_cell_moments_vec runs per thread)
+    N = len(xy)
+    e.assemble(1.0 + xy[:, 0], 0.5 - xy[:, 1])
+    ncells = nc * nc
+    want = np.zeros(N * 18 * ncells)
+    e.lib.emul_get_cell_scratch.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+    assert e.lib.emul_get_cell_scratch(e.h, dptr(want), want.size) == want.size
+
+    slots, t0, t1 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    dims = (C.c_int * 10)()
+    e.lib.emul_table_pointers.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 3 + [C.POINTER(C.c_int)]
+    e.lib.emul_table_pointers(e.h, C.byref(slots), C.byref(t0), C.byref(t1), dims)
+    e.lib.emul_mesh_h.restype = C.c_double
+    e.lib.emul_mesh_h.argtypes = [C.c_void_p]
+    got = np.zeros_like(want)
+    flag = C.c_int(0)
+    scale = 1.0  # D_2 of the bio sets used here is 1, elliptic always 1
+    lib.host_run.argtypes = [C.POINTER(C.c_int), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                             C.c_void_p, C.POINTER(C.c_int)]
+    lib.host_run(dims, e.lib.emul_mesh_h(e.h), slots, t0, t1, N, scale, dptr(got), C.byref(flag))
+    assert flag.value == 0
+    assert np.abs(want).max() > 0
+    assert np.array_equal(got, want)
+    e.close()
+
+
+def _nvrtc():
+    for name in ("libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"):
+        try:
+            return C.CDLL(name)
+        except OSError:
+            continue
+    return None
+
+
+@pytest.mark.parametrize("problem,prm", [("bio", "biocase.prm"), ("bio", "biocase-curved.prm"),
+                                         ("elliptic", "elliptic_non_linear.prm")])
+def test_nvrtc_accepts_the_generated_kernel(problem, prm):
+    nv = _nvrtc()
+    if nv is None:
+        pytest.skip("NVRTC not installed")
+    e, _ = _emul(problem, prm, 4, 12)
+    src = _source(e)
+    prog = C.c_void_p()
+    assert nv.nvrtcCreateProgram(C.byref(prog), src.encode(), b"msgpu_jit.cu", 0, None, None) == 0
+    opts = [b"--gpu-architecture=sm_100a", b"--std=c++17", b"-lineinfo"]
+    rc = nv.nvrtcCompileProgram(prog, len(opts), (C.c_char_p * len(opts))(*opts))
+    size = C.c_size_t()
+    nv.nvrtcGetProgramLogSize(prog, C.byref(size))
+    log = C.create_string_buffer(size.value)
+    nv.nvrtcGetProgramLog(prog, log)
+    assert rc == 0, log.value.decode()
+    nv.nvrtcGetCUBINSize(prog, C.byref(size))
+    assert size.value > 1000
+    nv.nvrtcDestroyProgram(C.byref(prog))
+    e.close()
