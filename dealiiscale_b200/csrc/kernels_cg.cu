@@ -19,6 +19,8 @@
 // alpha = gh/(d.h); x += alpha d; g += alpha h; res = |g|; stop if res <= tol;
 // beta = res^2/gh; d = beta d - g }.  Dot products use a fixed shuffle tree + fixed order over
 // warps, so results are bit-reproducible from run to run and independent of the SM.
+#include <cooperative_groups.h>
+
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -743,6 +745,238 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
 }
 
 // -------------------------------------------------------------------------------------------
+// Cluster CG for systems that do not fit one SM (m > 67, e.g. the 128 x 128-cell micro meshes).
+//
+// A thread-block cluster of CL CTAs owns one system; CTA c keeps rows [c*RC, (c+1)*RC) exactly as
+// k_cg_strip_tmem keeps a whole system: seven matrix entries per row in its SM's tensor memory, M1
+// and its window of the search direction in shared memory, x / g / d / h strips in registers.
+// What crosses CTAs:
+//   * the halo of d: after every update a CTA stores its first / last `pad` entries straight into
+//     the neighbours' shared memory (distributed shared memory, plain stores through
+//     cluster.map_shared_rank);
+//   * the two dot products per step: every CTA reduces its rows, stores the partial into slot
+//     [rank] of every CTA's `cred` array, and after the cluster barrier all CTAs add the CL partials
+//     in rank order — every CTA sees bit-identical scalars, so the stop decision is uniform.
+// Three cluster barriers per CG step (halo, two reductions) replace the three CTA barriers.
+namespace cg = cooperative_groups;
+
+template <int K, bool JACOBI>
+__global__ void __launch_bounds__(256, 1) k_cg_cluster(CgArgs a) {
+  constexpr int BT = 256, CW = 256, NACC = 4, RC = BT * K;
+  static_assert(14 * K + 2 <= CW, "strip must fit the TMEM columns of a thread");
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = static_cast<int>(cluster.num_blocks());
+  const int crank = static_cast<int>(cluster.block_rank());
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int s_k;
+  __shared__ uint32_t s_tmem;
+  const int n = a.md.n, m = a.md.m, ld = a.md.ld;
+  const int pad = tmem_pad(m, K);
+  const int win = RC + 2 * pad;            // window of this CTA: local index i in [-pad, RC + pad)
+  const int lo = crank * RC;               // first global row of this CTA
+  const int nloc = n - lo < RC ? (n - lo > 0 ? n - lo : 0) : RC;
+  double* const m1 = sm + pad;             // M1[lo + i]
+  double* const dv = sm + win + pad;       // d[lo + i]
+  double* const red = sm + 2 * win;        // 3 x 32 warp partials (16-byte aligned: 2*win is even)
+  double* const cred = red + 96;           // 3 x 8 CTA partials
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int r0 = tid * K;                                         // local
+  const int rc0 = r0 < nloc ? r0 : nloc;                          // dead threads sit on the zero guard
+  const int nlive = r0 < nloc ? (nloc - r0 < K ? nloc - r0 : K) : 0;
+  double* const dv_prev = crank > 0 ? cluster.map_shared_rank(dv, crank - 1) : nullptr;
+  double* const dv_next = crank + 1 < CL ? cluster.map_shared_rank(dv, crank + 1) : nullptr;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(
+        static_cast<uint32_t>(__cvta_generic_to_shared(&s_tmem))));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  for (int i = tid; i < win; i += BT) dv[i - pad] = 0.0;  // entries nobody writes stay zero (guards past n)
+  asm volatile("tcgen05.fence::before_thread_sync;\n");
+  cluster.sync();
+  asm volatile("tcgen05.fence::after_thread_sync;\n");
+  const uint32_t tbase =
+      s_tmem + ((static_cast<uint32_t>(warp & 3) * 32u) << 16) + static_cast<uint32_t>(warp >> 2) * static_cast<uint32_t>(CW);
+
+  // own entries of d -> shared memory, border entries also into the neighbours' halos
+  auto publish = [&](const double (&dl)[K]) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      if (j < nlive) {
+        const int i = r0 + j;
+        dv[i] = dl[j];
+        if (dv_prev && i < pad) dv_prev[RC + i] = dl[j];
+        if (dv_next && i >= nloc - pad) dv_next[i - nloc] = dl[j];
+      }
+    }
+  };
+
+  auto spmv_strip = [&](const double (&dl)[K], double (&hh)[K]) {
+    double ra = dv[rc0 + m - 1], rb = dv[rc0 + m];
+    double la = dv[rc0 - m - 1], lb = dv[rc0 - m];
+    double below = dv[rc0 - 1];
+    double m1_prev = m1[rc0 - 1];
+    TmemRow q[2];
+    tmem_issue_row(tbase, q[0]);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int r = rc0 + j;
+      TmemRow& cur = q[j & 1];
+      tmem_wait_row(cur);
+      if (j + 1 < K) tmem_issue_row(tbase + 14u * (j + 1), q[(j + 1) & 1]);
+      const double rc = dv[r + m + 1], lc = dv[r - m + 1];
+      const double m1r = m1[r];
+      const double above = (j + 1 < K) ? dl[j + 1] : dv[r + 1];
+      double s = tmem_get(cur, 0) * dl[j];
+      double t = tmem_get(cur, 1) * ra;
+      s += m1r * above;
+      t += tmem_get(cur, 4) * lc;
+      s += m1_prev * below;
+      t += tmem_get(cur, 2) * rb;
+      s += tmem_get(cur, 5) * lb;
+      t += tmem_get(cur, 3) * rc;
+      s += tmem_get(cur, 6) * la;
+      hh[j] = s + t;
+      ra = rb; rb = rc;
+      la = lb; lb = lc;
+      below = dl[j];
+      m1_prev = m1r;
+    }
+  };
+
+  // Sum over the whole cluster, identical in every thread of every CTA.  `buf` in {0,1,2}.
+  auto cluster_sum = [&](double part, int buf) -> double {
+    const double mine = block_sum_tree<BT>(part, red + 32 * buf);
+    if (tid < CL) cluster.map_shared_rank(cred + 8 * buf, tid)[crank] = mine;
+    cluster.sync();
+    double t = 0.0;
+    for (int c = 0; c < CL; ++c) t += cred[8 * buf + c];
+    return t;
+  };
+
+  for (;;) {
+    cluster.sync();  // every CTA is done with the previous system (its halos, cred, s_k)
+    if (crank == 0 && tid == 0) {
+      const int k = atomicAdd(a.work_counter, 1);
+      for (int c = 0; c < CL; ++c) *cluster.map_shared_rank(&s_k, c) = k;
+    }
+    cluster.sync();
+    const int k = s_k;
+    if (k >= a.N) break;
+
+    const double* dg = a.diag + static_cast<size_t>(k) * a.diag_stride;
+    for (int i = tid - pad; i < RC + pad; i += BT) {
+      const int g = lo + i;
+      m1[i] = (g >= 0 && g < n) ? __ldg(dg + ld + g) : 0.0;
+    }
+    double diag_own[JACOBI ? K : 1];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const bool in = j < nlive;
+      const int g = lo + r0 + j;
+      double v[7];
+      v[0] = in ? __ldg(dg + g) : 0.0;
+      v[1] = in ? __ldg(dg + 2 * static_cast<size_t>(ld) + g) : 0.0;
+      v[2] = in ? __ldg(dg + 3 * static_cast<size_t>(ld) + g) : 0.0;
+      v[3] = in ? __ldg(dg + 4 * static_cast<size_t>(ld) + g) : 0.0;
+      v[4] = (in && g - (m - 1) >= 0) ? __ldg(dg + 2 * static_cast<size_t>(ld) + g - (m - 1)) : 0.0;
+      v[5] = (in && g - m >= 0) ? __ldg(dg + 3 * static_cast<size_t>(ld) + g - m) : 0.0;
+      v[6] = (in && g - (m + 1) >= 0) ? __ldg(dg + 4 * static_cast<size_t>(ld) + g - (m + 1)) : 0.0;
+      if (JACOBI) diag_own[j] = in ? v[0] : 1.0;
+      tmem_store_row(tbase + 14u * j, v);
+    }
+
+    double xx[K], gg[K], dl[K], hh[K];
+    const double* bk = a.b + static_cast<size_t>(k) * n;
+    double* xk = a.x + static_cast<size_t>(k) * n;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      xx[j] = (j < nlive) ? xk[lo + r0 + j] : 0.0;
+      dl[j] = xx[j];
+    }
+    publish(dl);
+    cluster.sync();
+    spmv_strip(dl, hh);
+    double part = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      gg[j] = (j < nlive) ? (hh[j] - bk[lo + r0 + j]) : 0.0;
+      part += gg[j] * gg[j];
+    }
+    double res = sqrt(cluster_sum(part, 0));
+    int it = 0;
+    bool ok = res <= a.tol;
+    double gh = 0.0;
+    if (!ok) {
+      if (JACOBI) {
+        part = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const double z = gg[j] / diag_own[j];
+          dl[j] = -z;
+          part += gg[j] * z;
+        }
+        gh = cluster_sum(part, 1);
+      } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) dl[j] = -gg[j];
+        gh = res * res;
+      }
+      publish(dl);
+      for (;;) {
+        ++it;
+        cluster.sync();
+        spmv_strip(dl, hh);
+        part = strip_dot<K, NACC>([&](int j) { return dl[j] * hh[j]; });
+        const double alpha = gh / cluster_sum(part, 0);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          xx[j] += alpha * dl[j];
+          gg[j] += alpha * hh[j];
+        }
+        part = strip_dot<K, NACC>([&](int j) { return gg[j] * gg[j]; });
+        res = sqrt(cluster_sum(part, 1));
+        if (res <= a.tol) {
+          ok = true;
+          break;
+        }
+        if (it >= a.max_it || res != res) break;
+        double beta = gh;
+        if (JACOBI) {
+          part = 0.0;
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            hh[j] = gg[j] / diag_own[j];
+            part += gg[j] * hh[j];
+          }
+          gh = cluster_sum(part, 2);
+          beta = gh / beta;
+#pragma unroll
+          for (int j = 0; j < K; ++j) dl[j] = beta * dl[j] - hh[j];
+        } else {
+          gh = res * res;
+          beta = gh / beta;
+#pragma unroll
+          for (int j = 0; j < K; ++j) dl[j] = beta * dl[j] - gg[j];
+        }
+        publish(dl);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+      if (j < nlive) xk[lo + r0 + j] = xx[j];
+    if (crank == 0 && tid == 0) {
+      if (a.iters) a.iters[k] = it;
+      if (a.res) a.res[k] = res;
+      if (!ok) atomicExch(a.fail_flag, 1);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(s_tmem));
+  cluster.sync();  // no CTA may exit while a neighbour could still address its shared memory
+}
+
+// -------------------------------------------------------------------------------------------
 // Global-memory CG for systems that do not fit in one SM's shared memory (m > 67): the matrix is
 // streamed from L2/HBM every iteration, work vectors live in a per-CTA workspace.  Same
 // recurrence, same reduction order; kept simple — the cluster/DSMEM variant is the next step.
@@ -932,6 +1166,44 @@ int launch_strip_tmem(cudaStream_t s, const CgArgs& a, int num_sms) {
   return 1;
 }
 
+// Cluster variant: CL = ceil(n / (256*17)) CTAs per system, as many clusters as the GPU can hold.
+int launch_cluster(cudaStream_t s, const CgArgs& a, int num_sms) {
+  constexpr int K = 17, RC = 256 * K;
+  const int CL = (a.md.n + RC - 1) / RC;
+  if (CL < 1 || CL > 8) return -1;
+  const int pad = tmem_pad(a.md.m, K);
+  const size_t smem = (static_cast<size_t>(2) * (RC + 2 * pad) + 96 + 24) * sizeof(double);
+  auto kern = a.precond == 1 ? k_cg_cluster<K, true> : k_cg_cluster<K, false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+    return -1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cfg.gridDim = dim3(CL);
+  int clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess || clusters < 1) {
+    cudaGetLastError();
+    clusters = num_sms / CL / 2;
+    if (clusters < 1) clusters = 1;
+  }
+  if (clusters > a.N) clusters = a.N;
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters) * CL);
+  CgArgs args = a;
+  if (cudaLaunchKernelEx(&cfg, kern, args) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return 1;
+}
+
 template <int BT, int RPT>
 int launch_resident(cudaStream_t s, const CgArgs& a, int num_sms) {
   const size_t smem = resident_smem_bytes(a.md);
@@ -956,7 +1228,7 @@ int launch_cg(cudaStream_t s, const CgArgs& a, int num_sms, int* variant) {
   cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
   cudaMemsetAsync(a.fail_flag, 0, sizeof(int), s);
   const int n = a.md.n;
-  const bool fits = resident_smem_bytes(a.md) <= 227 * 1024;
+  const bool fits = resident_smem_bytes(a.md) <= 227 * 1024 && n <= 512 * 9;  // 512 x 9 rows is the largest strip shape
   const char* force = std::getenv("MSGPU_CG_VARIANT");  // "global" forces the streaming kernel (tests)
   if (fits && !(force && force[0] == 'g')) {
     if (variant) *variant = 0;
@@ -985,6 +1257,14 @@ int launch_cg(cudaStream_t s, const CgArgs& a, int num_sms, int* variant) {
     if (n <= 2560) return launch_resident<512, 5>(s, a, num_sms);
     if (wide && wide[0] == '1') return launch_resident<1024, 5>(s, a, num_sms);
     return launch_resident<512, 9>(s, a, num_sms);
+  }
+  const char* nocluster = std::getenv("MSGPU_CG_CLUSTER");  // "0": stream the matrix from L2/HBM instead (A/B)
+  if (!(force && force[0] == 'g') && !(nocluster && nocluster[0] == '0') && n > 2560 && n <= 8 * 256 * 17) {
+    const int r = launch_cluster(s, a, num_sms);
+    if (r > 0) {
+      if (variant) *variant = 4;
+      return r;
+    }
   }
   if (variant) *variant = 1;
   constexpr int BT = 512;

@@ -173,7 +173,8 @@ typedef struct {
   long long launches;  /* kernels launched by this context so far      */
   long long cg_iterations_total; /* sum over systems of the last solve */
   int cg_variant;      /* 0 = shared-memory resident (strided rows), 1 = global-memory, 2 = resident (row strips),
-                          3 = row strips with the matrix in tensor memory */
+                          3 = row strips with the matrix in tensor memory,
+                          4 = one system per thread-block cluster (2-8 SMs; systems with more than 67 nodes per axis) */
   int jit_kernels;     /* assembly kernels specialised at run time (NVRTC) for this problem; 0 = the
                           bytecode interpreter runs at every quadrature point (MSGPU_JIT=0, or no NVRTC) */
 } msgpu_stats;
