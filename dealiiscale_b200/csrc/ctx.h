@@ -18,10 +18,23 @@ namespace msgpu {
 enum Phase { PH_TABLES = 0, PH_MOMENTS, PH_GATHER, PH_CG, PH_COUPLING, PH_COUNT };
 enum FlagSlot { FLAG_JACOBIAN = 0, FLAG_COUNTER = 1, FLAG_CGFAIL = 2 };
 
+// Device-resident macro system(s), see macro.cu.
+struct MacroDevice {
+  int ready = 0, fields = 0;
+  MeshDims md{};
+  std::vector<int> ref2int;
+  double *d_diag = nullptr, *d_C = nullptr, *d_b0 = nullptr, *d_b = nullptr, *d_x = nullptr, *d_all = nullptr,
+         *d_res = nullptr;
+  int *d_ref2int = nullptr, *d_int2ref = nullptr, *d_iters = nullptr, *d_flags = nullptr;
+  int source[2] = {0, 1}, has_system[2] = {0, 0}, rhs_given[2] = {0, 0};
+};
+
 struct PendingTimer {
   int phase;
   cudaEvent_t a, b;
 };
+
+void macro_release(msgpu_ctx* ctx);
 
 }  // namespace msgpu
 
@@ -80,6 +93,9 @@ struct msgpu_ctx {
   std::vector<msgpu::PendingTimer> pending;
   double phase_ms[msgpu::PH_COUNT] = {0};
   long long launches = 0;
+
+  // macro system(s) on the device
+  msgpu::MacroDevice macro;
 
   // multi-GPU
   int comm_ready = 0, rank = 0, n_ranks = 1, n_total = 0, k_offset = 0;

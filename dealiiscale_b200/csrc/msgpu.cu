@@ -193,6 +193,7 @@ void msgpu_destroy(msgpu_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   drain_timers(ctx);
   comm_destroy(ctx);
+  macro_release(ctx);
   free_all(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

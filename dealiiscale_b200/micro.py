@@ -262,6 +262,37 @@ class MicroSolver:
         self._check(self.lib.msgpu_get_stats(self.h, C.byref(s), int(reset)))
         return {f: getattr(s, f) for f, _ in capi.Stats._fields_}
 
+    # ---- the macro system(s) on the device (include/msgpu.h, msgpu_macro_*) ----
+    def macro_setup(self, n_fields, mesh_kind, cells_per_axis):
+        self._check(self.lib.msgpu_macro_setup(self.h, int(n_fields), int(mesh_kind), int(cells_per_axis)))
+        self._macro_n = (cells_per_axis + 1) ** 2
+        self._macro_fields = n_fields
+
+    def macro_set_system(self, field, source, rowstart, col, A, C=None, b0=None, x0=None):
+        rs = np.ascontiguousarray(rowstart, dtype=np.int32)
+        cl = np.ascontiguousarray(col, dtype=np.int32)
+        keep = [np.ascontiguousarray(v, dtype=np.float64) if v is not None else None for v in (A, C, b0, x0)]
+        ptr = [_d(v) if v is not None else None for v in keep]
+        self._check(self.lib.msgpu_macro_set_system(self.h, int(field), int(source), _i(rs), _i(cl), *ptr))
+
+    def macro_set_rhs(self, field, b):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        self._check(self.lib.msgpu_macro_set_rhs(self.h, int(field), _d(b)))
+
+    def macro_set_solution(self, field, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self._check(self.lib.msgpu_macro_set_solution(self.h, int(field), _d(x)))
+
+    def macro_get_solution(self, field):
+        out = np.zeros(self._macro_n)
+        self._check(self.lib.msgpu_macro_get_solution(self.h, int(field), _d(out)))
+        return out
+
+    def macro_solve(self, tol=1e-12, max_it=10000, adopt=True):
+        its = np.zeros(self._macro_fields, dtype=np.int32)
+        self._check(self.lib.msgpu_macro_solve(self.h, C.c_double(tol), int(max_it), int(adopt), _i(its)))
+        return its
+
     def jit_log(self) -> str:
         """Why the run-time specialised kernels are not in use ('' when they are)."""
         return self.lib.msgpu_jit_log(self.h).decode()

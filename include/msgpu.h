@@ -163,6 +163,31 @@ int msgpu_comm_init(msgpu_ctx* ctx, const char id[128], int rank, int n_ranks, i
 /* Broadcast of the macro solution from root; every rank keeps its own block (set_macro_solution). */
 int msgpu_broadcast_macro(msgpu_ctx* ctx, double* u_all, double* w_all, int root);
 
+/* ---- the macro system(s) on the device -------------------------------------
+ * Replaces MacroSolver::assemble_system + solve (src/elliptic-elliptic/macro.cpp:57-114,
+ * src/bio-multiscale/macro.cpp:100-202) and the solve of PiSolver (src/elliptic-parabolic/pi_solver.cpp:124-149)
+ * for the cycles after the first: the macro matrix never changes and its load is affine in the micro
+ * contribution, b(c) = b0 + C c.  The macro mesh is the mesh of the grid locations: it must have exactly
+ * one DoF per micro system (all ranks' systems when a communicator is attached), in deal.II numbering.
+ *   msgpu_macro_setup       1 or 2 fields on a (cells_per_axis)^2 mesh of the given kind
+ *   msgpu_macro_set_system  per field: A (after MatrixTools::apply_boundary_values; symmetric), C and b0 as
+ *                           CSR values on one 9-point pattern (rowstart/col in deal.II numbering, any
+ *                           column order); `source` = which coupling vector c is (0: c0, 1: c1 of
+ *                           msgpu_coupling); x0 = start vector (Dirichlet values in place), may be NULL
+ *   msgpu_macro_set_rhs     a host-assembled right-hand side for the NEXT solve only (PiSolver: its
+ *                           load is a product of two finite-element functions)
+ *   msgpu_macro_solve       b = b0 + C c from the device-resident result of the last msgpu_coupling,
+ *                           SolverCG as msgpu_solve (warm start), and, if adopt != 0, the solution
+ *                           becomes the macro solution of this rank's micro systems (field 0 -> u,
+ *                           field 1 -> w) without a host round trip; iters[n_fields] may be NULL      */
+int msgpu_macro_setup(msgpu_ctx* ctx, int n_fields, int mesh_kind, int cells_per_axis);
+int msgpu_macro_set_system(msgpu_ctx* ctx, int field, int source, const int* rowstart, const int* col,
+                           const double* A, const double* C, const double* b0, const double* x0);
+int msgpu_macro_set_rhs(msgpu_ctx* ctx, int field, const double* b);
+int msgpu_macro_set_solution(msgpu_ctx* ctx, int field, const double* x);
+int msgpu_macro_get_solution(msgpu_ctx* ctx, int field, double* x);
+int msgpu_macro_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int adopt, int* iters);
+
 /* ---- measurement hooks ------------------------------------------------------------------- */
 typedef struct {
   double ms_tables;    /* slot + line table kernels                    */
