@@ -41,12 +41,25 @@ class MacroSolver {
   void set_micro_objects(MicroSolver* m) { micro = m; }
   // integrate_micro_cells for every macro DoF (macro.cpp:254-306): one coupling kernel
   void compute_microscopic_contribution() { micro->coupling(micro_contribution_u, &micro_contribution_w); }
-  void assemble_system() {  // macro.cpp:100-192
+  // both macro matrices are constant and both loads affine in the flux integrals
+  // ((-uc + fu), (-wc + fw) below), so after one host assembly the two systems live on the device.
+  void enable_device() {
+    std::fill(micro_contribution_u.begin(), micro_contribution_u.end(), 0.0);
+    std::fill(micro_contribution_w.begin(), micro_contribution_w.end(), 0.0);
+    assemble_system(false);
+    CsrMatrix Cu = mass_operator(mesh, 8, -1.0), Cw = mass_operator(mesh, 8, -1.0);
+    zero_rows(Cu, boundary_values);
+    micro->macro_setup(2, MSGPU_MESH_SUBDIVIDED, n_cells);
+    micro->macro_set_system(0, 0, mesh, system_matrix_u, &Cu, system_rhs_u, sol_u);
+    micro->macro_set_system(1, 1, mesh, system_matrix_w, &Cw, system_rhs_w, sol_w);
+    on_device = true;
+  }
+  void assemble_system(bool fetch_contribution = true) {  // macro.cpp:100-192
     system_matrix_u.zero();
     system_matrix_w.zero();
     std::fill(system_rhs_u.begin(), system_rhs_u.end(), 0.0);
     std::fill(system_rhs_w.begin(), system_rhs_w.end(), 0.0);
-    compute_microscopic_contribution();
+    if (fetch_contribution) compute_microscopic_contribution();
     Quadrature Q(8);
     const double h = mesh.h;
     const double k_1 = pde_data.data.constants.at("kappa_1"), k_3 = pde_data.data.constants.at("kappa_3");
@@ -110,7 +123,7 @@ class MacroSolver {
         system_rhs_w[cd[a]] += bw[a];
       }
     }
-    std::map<int, double> boundary_values;  // u only, on |x0| = 1 (macro.cpp:189-191)
+    boundary_values.clear();  // u only, on |x0| = 1 (macro.cpp:189-191)
     for (int d = 0; d < mesh.n; ++d)
       if (mesh.dof_ix[d] == 0 || mesh.dof_ix[d] == mesh.m - 1)
         boundary_values[d] = pde_data.bc_u_1.value(mesh.x_of(d), mesh.y_of(d));
@@ -123,6 +136,15 @@ class MacroSolver {
     solve_cg(system_matrix_w, sol_w, system_rhs_w, 10000, 1e-12);
   }
   void assemble_and_solve() {
+    if (on_device) {
+      compute_microscopic_contribution();  // integrals stay on the device; host copies are for the records
+      old_sol_u = sol_u;
+      old_sol_w = sol_w;
+      micro->macro_solve(1e-12, 10000, true);
+      micro->macro_get_solution(0, sol_u);
+      micro->macro_get_solution(1, sol_w);
+      return;
+    }
     assemble_system();
     solve();
   }
@@ -147,7 +169,9 @@ class MacroSolver {
   unsigned int n_cells;
   CsrMatrix system_matrix_u, system_matrix_w;
   std::vector<double> system_rhs_u, system_rhs_w;
+  std::map<int, double> boundary_values;
   MicroSolver* micro = nullptr;
+  bool on_device = false;
 };
 
 struct CycleRecord {
@@ -189,6 +213,7 @@ class Manager {
     micro_solver.setup();
     micro_solver.set_macro_solution(&macro_solver.sol_u, &macro_solver.sol_w);
     macro_solver.set_micro_objects(&micro_solver);
+    if (device_macro_enabled()) macro_solver.enable_device();
     cycle = 0;
     old_residual = 0;
     residual = 1;

@@ -37,9 +37,20 @@ class MacroSolver {
   void set_micro_objects(MicroSolver* m) { micro = m; }  // macro.cpp:128-131
   // get_micro_bulk for every macro DoF (macro.cpp:134-166) is one coupling kernel on the device
   void compute_microscopic_contribution() { micro->coupling(micro_contribution); }
-  void assemble_system() {  // macro.cpp:57-106
+  // the macro matrix never changes and the load is affine in the micro contribution,
+  // so after one host assembly (contribution = 0) the system lives on the device.
+  void enable_device() {
+    std::fill(micro_contribution.begin(), micro_contribution.end(), 0.0);
+    assemble_system(false);
+    CsrMatrix C = mass_operator(mesh, 8, 1.0);
+    zero_rows(C, boundary_values);
+    micro->macro_setup(1, MSGPU_MESH_REFINE_GLOBAL, 1 << refine_level);
+    micro->macro_set_system(0, 0, mesh, system_matrix, &C, system_rhs, solution);
+    on_device = true;
+  }
+  void assemble_system(bool fetch_contribution = true) {  // macro.cpp:57-106
     Quadrature Q(8);
-    compute_microscopic_contribution();
+    if (fetch_contribution) compute_microscopic_contribution();
     system_matrix.zero();
     std::fill(system_rhs.begin(), system_rhs.end(), 0.0);
     const double h = mesh.h;
@@ -66,7 +77,7 @@ class MacroSolver {
         system_rhs[cd[a]] += b[a];
       }
     }
-    std::map<int, double> boundary_values;
+    boundary_values.clear();
     for (int d = 0; d < mesh.n; ++d)
       if (mesh.on_boundary(d)) boundary_values[d] = pde_data.macro_bc.value(mesh.x_of(d), mesh.y_of(d));
     apply_boundary_values(boundary_values, system_matrix, solution, system_rhs);
@@ -76,6 +87,13 @@ class MacroSolver {
     std::printf("\t %d CG iterations to convergence (macro)\n", last_iterations);
   }
   void run() {  // macro.cpp:177-181
+    if (on_device) {
+      compute_microscopic_contribution();  // leaves the integrals on the device; the host copy is for the records
+      last_iterations = micro->macro_solve(1e-12, 1000, true)[0];
+      micro->macro_get_solution(0, solution);
+      std::printf("\t %d CG iterations to convergence (macro)\n", last_iterations);
+      return;
+    }
     assemble_system();
     solve();
   }
@@ -90,7 +108,9 @@ class MacroSolver {
   unsigned int refine_level;
   CsrMatrix system_matrix;
   std::vector<double> system_rhs;
+  std::map<int, double> boundary_values;
   MicroSolver* micro = nullptr;
+  bool on_device = false;
 };
 
 struct CycleRecord {
@@ -127,6 +147,7 @@ class Manager {
     micro_solver.setup();
     micro_solver.set_macro_solution(&macro_solver.solution);
     macro_solver.set_micro_objects(&micro_solver);
+    if (device_macro_enabled()) macro_solver.enable_device();
     cycle = 0;
   }
   void run() {  // manager.cpp:37-51

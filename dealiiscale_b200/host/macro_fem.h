@@ -7,6 +7,7 @@
 // Macro functions of (x0,x1[,t]) are compiled with the same expression compiler as the micro
 // functions and evaluated by running the VM on the host (expr_vm.cuh is host/device code).
 #pragma once
+#include <cstdlib>
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -227,6 +228,37 @@ inline void shape_grad(double xi, double eta, double h, double g[4][2]) {
   g[1][0] = (1 - eta) / h;  g[1][1] = -xi / h;
   g[2][0] = -eta / h;       g[2][1] = (1 - xi) / h;
   g[3][0] = eta / h;        g[3][1] = xi / h;
+}
+
+// sign * int phi_a phi_b with QGauss(q) on every cell: the operator C of  b(c) = b0 + C c  when the
+// interpolated micro contribution enters a macro load linearly (macro.cpp:78-93, bio macro.cpp:144-165).
+inline CsrMatrix mass_operator(const MacroMesh& mesh, int q, double sign) {
+  CsrMatrix C;
+  C.reinit(mesh);
+  Quadrature Q(q);
+  const double h = mesh.h;
+  double M[4][4] = {};
+  for (int j = 0; j < q; ++j)
+    for (int i = 0; i < q; ++i) {
+      double v[4];
+      shape(Q.pt[i], Q.pt[j], v);
+      const double jxw = Q.wt[i] * Q.wt[j] * h * h;
+      for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) M[a][b] += sign * v[a] * v[b] * jxw;
+    }
+  for (const auto& cd : mesh.cell_dofs)
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 4; ++b) C.add(cd[a], cd[b], M[a][b]);
+  return C;
+}
+inline void zero_rows(CsrMatrix& C, const std::map<int, double>& rows) {
+  for (const auto& r : rows)
+    for (int k = C.mesh->rowstart[r.first]; k < C.mesh->rowstart[r.first + 1]; ++k) C.val[k] = 0.0;
+}
+// MSGPU_HOST_MACRO=1 keeps the macro systems on the host (A/B against the device path)
+inline bool device_macro_enabled() {
+  const char* e = std::getenv("MSGPU_HOST_MACRO");
+  return !(e && e[0] == '1');
 }
 
 // || sum_k values[k] phi_k ||_{L2} with QGauss(q): integrate_difference(.., ZeroFunction, L2_norm)

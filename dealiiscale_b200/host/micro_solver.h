@@ -114,12 +114,30 @@ class MicroSolver {
     out.assign(static_cast<size_t>(num_grids_) * n_dofs_, 0.0);
     check(msgpu_get_solutions(ctx_, 0, num_grids_, out.data()));
   }
+  // ---- the macro system(s) on the device (include/msgpu.h, msgpu_macro_*) ----
+  void macro_setup(int n_fields, int mesh_kind, int cells_per_axis) {
+    check(msgpu_macro_setup(ctx_, n_fields, mesh_kind, cells_per_axis));
+    macro_fields_ = n_fields;
+  }
+  void macro_set_system(int field, int source, const MacroMesh& mesh, const CsrMatrix& A, const CsrMatrix* C,
+                        const std::vector<double>& b0, const std::vector<double>& x0) {
+    check(msgpu_macro_set_system(ctx_, field, source, mesh.rowstart.data(), mesh.col.data(), A.val.data(),
+                                 C ? C->val.data() : nullptr, b0.data(), x0.data()));
+  }
+  void macro_set_rhs(int field, const std::vector<double>& b) { check(msgpu_macro_set_rhs(ctx_, field, b.data())); }
+  void macro_set_solution(int field, const std::vector<double>& x) { check(msgpu_macro_set_solution(ctx_, field, x.data())); }
+  void macro_get_solution(int field, std::vector<double>& x) { check(msgpu_macro_get_solution(ctx_, field, x.data())); }
+  std::vector<int> macro_solve(double tol, int max_it, bool adopt) {
+    std::vector<int> its(macro_fields_, 0);
+    check(msgpu_macro_solve(ctx_, tol, max_it, adopt ? 1 : 0, its.data()));
+    return its;
+  }
   msgpu_ctx* context() { return ctx_; }
   std::vector<int> iterations;  // CG steps of every grid in the last solve
 
  private:
   msgpu_ctx* ctx_ = nullptr;
-  int problem_, cells_, n_dofs_ = 0, num_grids_ = 0;
+  int problem_, cells_, n_dofs_ = 0, num_grids_ = 0, macro_fields_ = 0;
   const std::vector<double>*macro_u_ = nullptr, *macro_w_ = nullptr;
   void push_macro() {
     if (!macro_u_) throw std::runtime_error("set_macro_solution was not called");

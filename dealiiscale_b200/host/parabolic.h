@@ -102,7 +102,25 @@ class PiSolver {
       if (mesh.on_boundary(d)) boundary_values[d] = pde_data.macro_bc.value(mesh.x_of(d), mesh.y_of(d));
     apply_boundary_values(boundary_values, system_matrix, solution, system_rhs);
   }
-  void solve() { last_iterations = solve_cg(system_matrix, solution, system_rhs, 10000, 1e-12); }
+  // A * Laplace with Dirichlet elimination is constant; the load (a product of two
+  // finite-element functions, :96-117) is assembled on the host and only the solve runs on the device.
+  void enable_device() {
+    assemble_system();
+    const std::vector<double> zero(mesh.n, 0.0);
+    micro->macro_setup(1, MSGPU_MESH_SUBDIVIDED, h_inv);
+    micro->macro_set_system(0, 0, mesh, system_matrix, nullptr, zero, solution);
+    on_device = true;
+  }
+  void solve() {
+    if (on_device) {
+      micro->macro_set_solution(0, solution);  // boundary values may move with t (apply_boundary_values set them)
+      micro->macro_set_rhs(0, system_rhs);
+      last_iterations = micro->macro_solve(1e-12, 10000, false)[0];
+      micro->macro_get_solution(0, solution);
+      return;
+    }
+    last_iterations = solve_cg(system_matrix, solution, system_rhs, 10000, 1e-12);
+  }
   double solution_difference() const {  // pi_solver.cpp:267-277
     std::vector<double> d(mesh.n);
     for (int i = 0; i < mesh.n; ++i) d[i] = solution[i] - old_solution[i];
@@ -138,6 +156,7 @@ class PiSolver {
   std::vector<double> system_rhs, macro_contribution;
   MicroSolver* micro = nullptr;
   int count = 0;
+  bool on_device = false;
 };
 
 struct StepRecord {
@@ -175,6 +194,7 @@ class TimeManager {
     rho_solver.setup();
     rho_solver.set_macro_solution(&pi_solver.solution);
     pi_solver.set_micro_solutions(&rho_solver);
+    if (device_macro_enabled()) pi_solver.enable_device();
     it = 0;
   }
   void run() {  // time_manager.cpp:41-62

@@ -135,3 +135,32 @@ def test_cli_binaries_run_and_write_the_table(tmp_path):
     assert "Results: 'macro_refinement', 'micro_refinement', 'num_threads', 'wall_time', 'cpu_time'" in r.stdout
     table = open(os.path.join(tmp_path, "results", "out.txt")).read()
     assert table.split()[:7] == ["cycle", "cells", "dofs", "mL2", "mH1", "ML2", "MH1"]
+
+
+def test_device_and_host_macro_paths_agree():
+    """the drivers keep the macro systems on the device by default
+    (msgpu_macro_*); MSGPU_HOST_MACRO=1 solves them on the host as the reference does."""
+    lib = _drivers()
+    prm, cells, limit = "linear.prm", (4, 8), 4
+    out = {}
+    for name, env in (("device", None), ("host", "1")):
+        if env:
+            os.environ["MSGPU_HOST_MACRO"] = env
+        try:
+            h = C.c_void_p(lib.msdrv_bio_create(_path(prm), *cells))
+            assert h.value, lib.msdrv_last_error()
+            n_cycles = lib.msdrv_bio_run(h, limit)
+            N, n = C.c_int(), C.c_int()
+            lib.msdrv_bio_sizes(h, C.byref(N), C.byref(n))
+            N, n = N.value, n.value
+            sc = np.zeros(6)
+            u, w, cu, cw = np.zeros(N), np.zeros(N), np.zeros(N), np.zeros(N)
+            micro, its = np.zeros((N, n)), np.zeros(N, dtype=np.int32)
+            lib.msdrv_bio_history(h, n_cycles - 1, dptr(sc), dptr(u), dptr(w), dptr(cu), dptr(cw), dptr(micro), iptr(its))
+            out[name] = (n_cycles, u.copy(), w.copy(), micro.copy())
+            lib.msdrv_bio_destroy(h)
+        finally:
+            os.environ.pop("MSGPU_HOST_MACRO", None)
+    assert out["device"][0] == out["host"][0]
+    for a, b in zip(out["device"][1:], out["host"][1:]):
+        assert rel_l2(a, b) < 1e-10
