@@ -246,8 +246,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the micro path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     distributed = world > 1
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL would print its version banner on stdout, ahead of the JSON line
+    # NCCL prints its version banner (and any debug output) on stdout, ahead of the JSON line: send it to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
