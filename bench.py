@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--micro-ref", type=int, default=6, help="micro refinement: 2^r cells per axis")
     ap.add_argument("--cpu-sample", type=int, default=0, help="micro systems in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-allgather", action="store_true",
+                    help="multi-GPU: exchange the flux integrals with ncclAllGather instead of the fused peer-memory kernel")
     return ap.parse_args()
 
 
@@ -224,8 +226,10 @@ def workload_config(args, n_gpus):
         "prm": args.prm, "micro_cells_per_axis": mc, "micro_dofs": (mc + 1) ** 2, "q_degree": 12,
         "macro_points_per_gpu": (Mc + 1) ** 2, "macro_points_total": (Mc + 1) ** 2 * n_gpus,
         "cg": "deal.II recurrence, identity preconditioner, abs tol 1e-12, max 10000",
-        "parallelism": f"macro points sharded over {n_gpus} GPU(s), allgather+broadcast per step" if n_gpus > 1
-                       else "single GPU",
+        "parallelism": (f"macro points sharded over {n_gpus} GPU(s); flux integrals exchanged "
+                        + ("with ncclAllGather" if args.nccl_allgather else
+                           "by the coupling kernel itself (peer-memory stores over NVLink + flag per peer)")
+                        + "; e2e adds an ncclBroadcast of the macro iterate per step") if n_gpus > 1 else "single GPU",
         "l2": "inputs larger than L2: 0.7 GB of matrix values + 1.9 GB of cell moments per step",
     }
 
@@ -273,6 +277,10 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         ms.attach_communicator(ids[0], rank, n_gpus, n_total)
     ms.setup()
+    if distributed and not args.nccl_allgather:
+        handles = [None] * n_gpus
+        dist.all_gather_object(handles, ms.p2p_export())
+        ms.p2p_attach(handles)
     n = ms.n_dofs
     m = micro_cells + 1
     nnz = (3 * m - 2) ** 2

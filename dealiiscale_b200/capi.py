@@ -26,7 +26,8 @@ EXPORTED = [
     "msgpu_zero_solutions", "msgpu_get_rhs", "msgpu_get_dof_permutation", "msgpu_get_dof_points", "msgpu_get_matrix_dense",
     "msgpu_comm_unique_id", "msgpu_partition", "msgpu_comm_init", "msgpu_broadcast_macro", "msgpu_enable_timing",
     "msgpu_get_stats", "msgpu_jit_log", "msgpu_macro_setup", "msgpu_macro_set_system", "msgpu_macro_set_rhs",
-    "msgpu_macro_set_solution", "msgpu_macro_get_solution", "msgpu_macro_solve",
+    "msgpu_macro_set_solution", "msgpu_macro_get_solution", "msgpu_macro_solve", "msgpu_comm_p2p_export",
+    "msgpu_comm_p2p_attach",
 ]
 
 

@@ -11,6 +11,7 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types only: the library is resolved at run time, see nccl_api()
 
+#include <cstdint>
 #include <cstring>
 
 #include "ctx.h"
@@ -82,6 +83,10 @@ int comm_ensure_buffers(msgpu_ctx* ctx) {
 // In-place allgather of this rank's block(s) of d_c.  Layout: c0 at [0, padded), c1 at [padded, 2*padded).
 int comm_allgather_coupling(msgpu_ctx* ctx, double*, double*) {
   ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm);
+  if (!comm) {
+    ctx->err = "no NCCL communicator and no peer-memory exchange attached";
+    return MSGPU_ERR_COMM;
+  }
   const int B = comm_block(ctx);
   const size_t padded = static_cast<size_t>(B) * ctx->n_ranks;
   const int fields = ctx->desc.problem == MSGPU_BIO ? 2 : 1;
@@ -99,7 +104,70 @@ int comm_allgather_coupling(msgpu_ctx* ctx, double*, double*) {
   return MSGPU_OK;
 }
 
+// ---- peer-memory exchange ---------------------------------------------------------------------
+// Every rank owns one exchange buffer: data[2 parities][2 fields][padded] doubles followed by one
+// 32-bit flag per rank.  k_coupling (kernels_cg.cu) stores each integral into the data area of ALL
+// ranks through peer-mapped pointers (NVLink / NVSwitch stores) and its last CTA writes the call
+// number into flag[this rank] of every peer.  The consumer side is a stream memory operation
+// (cuStreamWaitValue32, >=) on its own flags — no host synchronisation, no spinning kernel — followed
+// by kernels / copies that read the parity just completed in place.  Two parities are enough: a rank
+// can only be one call ahead of a peer, because its own wait needs that peer's flag of the same call.
+namespace {
+size_t p2p_padded(const msgpu_ctx* ctx) { return static_cast<size_t>(comm_block(ctx)) * ctx->n_ranks; }
+size_t p2p_bytes(const msgpu_ctx* ctx) { return 4 * p2p_padded(ctx) * sizeof(double) + 64 * sizeof(unsigned int); }
+unsigned int* p2p_flags(const msgpu_ctx* ctx, void* base) {
+  return reinterpret_cast<unsigned int*>(static_cast<char*>(base) + 4 * p2p_padded(ctx) * sizeof(double));
+}
+typedef int (*WaitValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+}  // namespace
+
+void comm_p2p_fill(msgpu_ctx* ctx, CouplingArgs& a) {
+  a.n_peers = 0;
+  if (!ctx->p2p_ready) return;
+  ctx->p2p_iter += 1;
+  const size_t padded = p2p_padded(ctx);
+  const size_t parity = ctx->p2p_iter & 1u;
+  a.n_peers = ctx->n_ranks;
+  for (int p = 0; p < ctx->n_ranks; ++p) {
+    double* data = static_cast<double*>(ctx->p2p_peer[p]) + parity * 2 * padded;
+    a.peer_c0[p] = data + ctx->k_offset;
+    a.peer_c1[p] = data + padded + ctx->k_offset;
+    a.peer_flag[p] = p2p_flags(ctx, ctx->p2p_peer[p]) + ctx->rank;
+  }
+  a.flag_value = ctx->p2p_iter;
+  a.done_counter = ctx->d_p2p_done;
+}
+
+int comm_p2p_collect(msgpu_ctx* ctx) {
+  const size_t padded = p2p_padded(ctx);
+  const size_t parity = ctx->p2p_iter & 1u;
+  WaitValue32Fn wait = reinterpret_cast<WaitValue32Fn>(ctx->wait_value_fn);
+  unsigned int* flags = p2p_flags(ctx, ctx->p2p_local);
+  for (int p = 0; p < ctx->n_ranks; ++p) {
+    if (p == ctx->rank) continue;  // this rank's own stores are ordered by the stream itself
+    const int rc = wait(ctx->stream, static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(flags + p)), ctx->p2p_iter,
+                        0u /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (rc != 0) {
+      ctx->err = "cuStreamWaitValue32 failed (" + std::to_string(rc) + ")";
+      return MSGPU_ERR_COMM;
+    }
+  }
+  // consumers read the parity just completed in place (no copy)
+  ctx->c_view = static_cast<const double*>(ctx->p2p_local) + parity * 2 * padded;
+  return MSGPU_OK;
+}
+
 void comm_destroy(msgpu_ctx* ctx) {
+  if (ctx->p2p_ready) {
+    cudaStreamSynchronize(ctx->stream);
+    for (int p = 0; p < ctx->n_ranks; ++p)
+      if (p != ctx->rank && ctx->p2p_peer[p]) cudaIpcCloseMemHandle(ctx->p2p_peer[p]);
+    ctx->p2p_ready = 0;
+  }
+  if (ctx->p2p_local) cudaFree(ctx->p2p_local);
+  if (ctx->d_p2p_done) cudaFree(ctx->d_p2p_done);
+  ctx->p2p_local = nullptr;
+  ctx->d_p2p_done = nullptr;
   if (ctx->nccl_comm) {
     nccl_api().CommDestroy(static_cast<ncclComm_t>(ctx->nccl_comm));
     ctx->nccl_comm = nullptr;
@@ -129,7 +197,7 @@ int msgpu_partition(int n_total, int n_ranks, int rank, int* k0, int* k1) {
 }
 
 int msgpu_comm_init(msgpu_ctx* ctx, const char id[128], int rank, int n_ranks, int n_total, int k_offset) {
-  if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return MSGPU_ERR_INVALID;
+  if (!ctx || n_ranks < 1 || n_ranks > 64 || rank < 0 || rank >= n_ranks) return MSGPU_ERR_INVALID;
   int k0, k1;
   msgpu_partition(n_total, n_ranks, rank, &k0, &k1);
   if (k_offset != k0 || (ctx->N != 0 && ctx->N != k1 - k0)) {
@@ -137,16 +205,18 @@ int msgpu_comm_init(msgpu_ctx* ctx, const char id[128], int rank, int n_ranks, i
     return MSGPU_ERR_INVALID;
   }
   if (cudaSetDevice(ctx->device) != cudaSuccess) return MSGPU_ERR_CUDA;
-  ncclUniqueId u;
-  std::memcpy(&u, id, 128);
-  ncclComm_t comm;
-  if (!nccl_api().ok) {
-    ctx->err = "libnccl.so.2 cannot be loaded";
-    return MSGPU_ERR_COMM;
+  if (id) {  // id == NULL: no NCCL communicator, the peer-memory exchange (msgpu_comm_p2p_*) must follow
+    ncclUniqueId u;
+    std::memcpy(&u, id, 128);
+    ncclComm_t comm;
+    if (!nccl_api().ok) {
+      ctx->err = "libnccl.so.2 cannot be loaded";
+      return MSGPU_ERR_COMM;
+    }
+    ncclResult_t r = nccl_api().CommInitRank(&comm, n_ranks, u, rank);
+    if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclCommInitRank");
+    ctx->nccl_comm = comm;
   }
-  ncclResult_t r = nccl_api().CommInitRank(&comm, n_ranks, u, rank);
-  if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclCommInitRank");
-  ctx->nccl_comm = comm;
   ctx->rank = rank;
   ctx->n_ranks = n_ranks;
   ctx->n_total = n_total;
@@ -157,11 +227,69 @@ int msgpu_comm_init(msgpu_ctx* ctx, const char id[128], int rank, int n_ranks, i
   return MSGPU_OK;
 }
 
+int msgpu_comm_p2p_export(msgpu_ctx* ctx, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!ctx || !ctx->comm_ready || !handle) return MSGPU_ERR_INVALID;
+  if (ctx->n_ranks > 8) {
+    ctx->err = "the peer-memory exchange supports up to 8 ranks";
+    return MSGPU_ERR_INVALID;
+  }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return MSGPU_ERR_CUDA;
+  if (!ctx->p2p_local) {
+    if (cudaMalloc(&ctx->p2p_local, p2p_bytes(ctx)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&ctx->d_p2p_done), sizeof(int)) != cudaSuccess) {
+      ctx->err = "cannot allocate the exchange buffer";
+      return MSGPU_ERR_CUDA;
+    }
+    cudaMemset(ctx->p2p_local, 0, p2p_bytes(ctx));
+    cudaMemset(ctx->d_p2p_done, 0, sizeof(int));
+  }
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, ctx->p2p_local) != cudaSuccess) {
+    ctx->err = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(cudaGetLastError());
+    return MSGPU_ERR_CUDA;
+  }
+  std::memcpy(handle, &h, 64);
+  return MSGPU_OK;
+}
+
+int msgpu_comm_p2p_attach(msgpu_ctx* ctx, const unsigned char* handles) {
+  if (!ctx || !ctx->comm_ready || !ctx->p2p_local || !handles) return MSGPU_ERR_INVALID;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return MSGPU_ERR_CUDA;
+  cudaDriverEntryPointQueryResult st;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &st) != cudaSuccess || !fn ||
+      st != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    ctx->err = "cuStreamWaitValue32 is not available";
+    return MSGPU_ERR_COMM;
+  }
+  ctx->wait_value_fn = fn;
+  for (int p = 0; p < ctx->n_ranks; ++p) {
+    if (p == ctx->rank) {
+      ctx->p2p_peer[p] = ctx->p2p_local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + static_cast<size_t>(p) * 64, 64);
+    if (cudaIpcOpenMemHandle(&ctx->p2p_peer[p], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      ctx->err = std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(p) + "): " + cudaGetErrorString(cudaGetLastError());
+      return MSGPU_ERR_COMM;
+    }
+  }
+  ctx->p2p_ready = 1;
+  return MSGPU_OK;
+}
+
 // u_all / w_all: [n_total] host arrays; significant on root, overwritten on the other ranks.
 int msgpu_broadcast_macro(msgpu_ctx* ctx, double* u_all, double* w_all, int root) {
   if (!ctx || !ctx->comm_ready || !ctx->setup_done || !u_all) return MSGPU_ERR_INVALID;
   if (cudaSetDevice(ctx->device) != cudaSuccess) return MSGPU_ERR_CUDA;
   ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm);
+  if (!comm) {
+    ctx->err = "msgpu_broadcast_macro needs the NCCL communicator (msgpu_comm_init with an id)";
+    return MSGPU_ERR_COMM;
+  }
   const size_t padded = static_cast<size_t>(comm_block(ctx)) * ctx->n_ranks;
   const int fields = w_all ? 2 : 1;
   double* host[2] = {u_all, w_all};

@@ -102,4 +102,12 @@ struct msgpu_ctx {
   void* nccl_comm = nullptr;
   size_t gather_capacity = 0;  // doubles available in d_c / d_macro
   std::vector<int> rank_counts, rank_offsets;
+  // peer-memory exchange (comm.cu): exchange buffer = data[2 parities][2 fields][padded] + flags[n_ranks]
+  int p2p_ready = 0;
+  unsigned int p2p_iter = 0;
+  void* p2p_local = nullptr;
+  void* p2p_peer[8] = {nullptr};
+  int* d_p2p_done = nullptr;
+  void* wait_value_fn = nullptr;
+  const double* c_view = nullptr;  // where the gathered coupling vectors of the last msgpu_coupling live
 };

@@ -131,6 +131,15 @@ struct CouplingArgs {
   double kappa_left, kappa_right;  // bio: kappa_2, kappa_4
   double* c0;           // [N] (already offset to this rank's block)
   double* c1;
+  // Peer-memory exchange (multi-GPU, comm.cu): when n_peers > 0 every integral is ALSO stored into the
+  // gather buffers of all ranks (peer-mapped pointers, already offset to this rank's block) and the last
+  // CTA to finish raises this rank's flag on every peer — compute and allgather in one kernel.
+  int n_peers;
+  double* peer_c0[8];
+  double* peer_c1[8];
+  unsigned int* peer_flag[8];
+  unsigned int flag_value;
+  int* done_counter;    // device int, zero between launches
 };
 int launch_coupling(cudaStream_t s, const CouplingArgs& a);
 

@@ -1088,29 +1088,50 @@ __global__ void __launch_bounds__(BT) k_cg_global(CgArgs a, double* __restrict__
 //   bio       c0 = sum_left  (-kappa_2 x jL + bcL),  c1 = sum_right (-kappa_4 x jR + bcR)
 __global__ void __launch_bounds__(128) k_coupling(CouplingArgs a) {
   const int warp = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= a.N) return;
   const int k = warp;
   const MeshDims& md = a.md;
-  const double* x = a.x + static_cast<size_t>(k) * md.n;
-  if (a.problem == PF_BIO) {
-    const double* edge = a.edge + static_cast<size_t>(k) * 4 * md.m;
-    double su = 0.0, sw = 0.0;
-    for (int iy = lane; iy < md.m; iy += 32) {
-      su += -a.kappa_left * x[iy] * edge[iy] + edge[2 * md.m + iy];
-      sw += -a.kappa_right * x[(md.m - 1) * md.m + iy] * edge[md.m + iy] + edge[3 * md.m + iy];
+  if (k < a.N) {
+    const double* x = a.x + static_cast<size_t>(k) * md.n;
+    if (a.problem == PF_BIO) {
+      const double* edge = a.edge + static_cast<size_t>(k) * 4 * md.m;
+      double su = 0.0, sw = 0.0;
+      for (int iy = lane; iy < md.m; iy += 32) {
+        su += -a.kappa_left * x[iy] * edge[iy] + edge[2 * md.m + iy];
+        sw += -a.kappa_right * x[(md.m - 1) * md.m + iy] * edge[md.m + iy] + edge[3 * md.m + iy];
+      }
+      su = warp_sum(su);
+      sw = warp_sum(sw);
+      if (lane == 0) {
+        a.c0[k] = su;
+        a.c1[k] = sw;
+        for (int p = 0; p < a.n_peers; ++p) {
+          a.peer_c0[p][k] = su;
+          a.peer_c1[p][k] = sw;
+        }
+      }
+    } else {
+      const double* jw = a.jw + static_cast<size_t>(k) * a.jw_stride;
+      double s = 0.0;
+      for (int r = lane; r < md.n; r += 32) s += x[r] * jw[r];
+      s = warp_sum(s);
+      if (lane == 0) {
+        a.c0[k] = s;
+        for (int p = 0; p < a.n_peers; ++p) a.peer_c0[p][k] = s;
+      }
     }
-    su = warp_sum(su);
-    sw = warp_sum(sw);
-    if (lane == 0) {
-      a.c0[k] = su;
-      a.c1[k] = sw;
+  }
+  if (a.n_peers > 0) {
+    // signal: all peer stores of this CTA are performed system-wide, then the last CTA raises the flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int done = atomicAdd(a.done_counter, 1);
+      if (done == static_cast<int>(gridDim.x) - 1) {
+        __threadfence_system();
+        for (int p = 0; p < a.n_peers; ++p) *reinterpret_cast<volatile unsigned int*>(a.peer_flag[p]) = a.flag_value;
+        *a.done_counter = 0;
+      }
     }
-  } else {
-    const double* jw = a.jw + static_cast<size_t>(k) * a.jw_stride;
-    double s = 0.0;
-    for (int r = lane; r < md.n; r += 32) s += x[r] * jw[r];
-    s = warp_sum(s);
-    if (lane == 0) a.c0[k] = s;
   }
 }
 

@@ -262,8 +262,9 @@ int msgpu_macro_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int adopt, int
   if (!(M.rhs_given[0] && (M.fields == 1 || M.rhs_given[1]))) {
     if (M.rhs_given[0] || M.rhs_given[1])
       return fail(ctx, MSGPU_ERR_INVALID, "macro: give the right-hand side of every field or of none");
-    k_macro_rhs<<<blocks, 128, 0, ctx->stream>>>(M.fields, n, M.md.ld, M.md.m, M.d_b0, M.d_C, M.d_int2ref, ctx->d_c,
-                                                 ctx->d_c + cfield, M.source[0], M.source[1], M.d_b);
+    if (!ctx->c_view) return fail(ctx, MSGPU_ERR_INVALID, "macro: msgpu_coupling has not been called yet");
+    k_macro_rhs<<<blocks, 128, 0, ctx->stream>>>(M.fields, n, M.md.ld, M.md.m, M.d_b0, M.d_C, M.d_int2ref, ctx->c_view,
+                                                 ctx->c_view + cfield, M.source[0], M.source[1], M.d_b);
     ++ctx->launches;
   }
   M.rhs_given[0] = M.rhs_given[1] = 0;

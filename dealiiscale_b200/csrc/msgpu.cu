@@ -142,6 +142,8 @@ int compute_residuals(msgpu_ctx* ctx, double* l2);
 int comm_allgather_coupling(msgpu_ctx* ctx, double* c0, double* c1);
 int comm_block(const msgpu_ctx* ctx);
 void comm_destroy(msgpu_ctx* ctx);
+void comm_p2p_fill(msgpu_ctx* ctx, CouplingArgs& a);
+int comm_p2p_collect(msgpu_ctx* ctx);
 }  // namespace msgpu
 
 extern "C" {
@@ -602,17 +604,22 @@ int msgpu_coupling(msgpu_ctx* ctx, double* c0, double* c1) {
     a.kappa_right = prob == MSGPU_BIO ? ctx->scalars[3] : 0.0;
     a.c0 = ctx->d_c + koff;          // written straight into this rank's block of the gather buffer
     a.c1 = ctx->d_c + field + koff;
+    ctx->c_view = ctx->d_c;
+    comm_p2p_fill(ctx, a);  // peer-memory exchange attached: the kernel also stores into every rank's buffer
     ctx->launches += launch_coupling(ctx->stream, a);
     CK(cudaGetLastError());
-    if (ctx->comm_ready) {
+    if (ctx->p2p_ready) {
+      int rc = comm_p2p_collect(ctx);
+      if (rc) return rc;
+    } else if (ctx->comm_ready) {
       int rc = comm_allgather_coupling(ctx, nullptr, nullptr);
       if (rc) return rc;
     }
   }
   if (!c0) return MSGPU_OK;
-  CK(cudaMemcpyAsync(c0, ctx->d_c, sizeof(double) * ntot, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(c0, ctx->c_view, sizeof(double) * ntot, cudaMemcpyDeviceToHost, ctx->stream));
   if (c1 && prob == MSGPU_BIO)
-    CK(cudaMemcpyAsync(c1, ctx->d_c + field, sizeof(double) * ntot, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(c1, ctx->c_view + field, sizeof(double) * ntot, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return MSGPU_OK;
 }

@@ -244,6 +244,17 @@ class MicroSolver:
         self.k_offset = k0
         self._check(self.lib.msgpu_comm_init(self.h, unique_id, rank, n_ranks, n_total, k0))
 
+    def p2p_export(self) -> bytes:
+        """Handle of this rank's exchange buffer (to be gathered from all ranks by the host)."""
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.msgpu_comm_p2p_export(self.h, buf))
+        return buf.raw
+
+    def p2p_attach(self, handles):
+        """handles: one 64-byte handle per rank, in rank order.  coupling() then exchanges through peer memory."""
+        blob = b"".join(handles)
+        self._check(self.lib.msgpu_comm_p2p_attach(self.h, blob))
+
     def broadcast_macro(self, u_all, w_all=None, root=0):
         u_all = np.ascontiguousarray(u_all, dtype=np.float64)
         wp = None

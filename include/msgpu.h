@@ -160,6 +160,13 @@ int msgpu_comm_unique_id(char id[128]);
 /* The partition every rank must use: rank r owns [k0,k1) = [r*B, min((r+1)*B, n_total)), B = ceil(n_total/n_ranks). */
 int msgpu_partition(int n_total, int n_ranks, int rank, int* k0, int* k1);
 int msgpu_comm_init(msgpu_ctx* ctx, const char id[128], int rank, int n_ranks, int n_total, int k_offset);
+/* Peer-memory exchange over NVLink / NVSwitch (one process per GPU): after msgpu_comm_init (its id may
+ * be NULL when NCCL is not wanted at all) every rank exports the handle of its exchange buffer, the host
+ * distributes the n_ranks handles by any means, every rank attaches them.  From then on msgpu_coupling is
+ * ONE kernel that computes the integrals and stores them into the gather buffers of all ranks, signalled
+ * with a flag per peer and awaited with a stream memory operation; the NCCL allgather is gone. <= 8 ranks. */
+int msgpu_comm_p2p_export(msgpu_ctx* ctx, unsigned char handle[64]);
+int msgpu_comm_p2p_attach(msgpu_ctx* ctx, const unsigned char* handles /* [n_ranks][64] */);
 /* Broadcast of the macro solution from root; every rank keeps its own block (set_macro_solution). */
 int msgpu_broadcast_macro(msgpu_ctx* ctx, double* u_all, double* w_all, int root);
 
