@@ -328,8 +328,10 @@ MSGPU_HOSTDEV void body_gather(const GatherArgs& a, long long gtid) {
   const int ix = r / md.m, iy = r % md.m;
   const int k = a.k0 + kl;
   const double* cellk = a.cell + static_cast<size_t>(kl) * CELL_STRIDE * md.ncells;
+  const bool uniform = a.uniform_stiffness != 0;
   auto C = [&](int cx, int cy, int e) -> double {
-    return MSGPU_LDG(cellk + static_cast<size_t>(e) * md.ncells + cx * md.nc + cy);
+    const int c = (uniform && (e < 10 || e >= 14)) ? 0 : cx * md.nc + cy;
+    return MSGPU_LDG(cellk + static_cast<size_t>(e) * md.ncells + c);
   };
   double d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, load = 0, jw = 0;
   for (int dy = -1; dy <= 0; ++dy)

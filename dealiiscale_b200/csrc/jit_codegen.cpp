@@ -288,10 +288,23 @@ extern "C" __global__ void __launch_bounds__(128) k_cell_moments_jit(MeshDims md
   moments_to_local(acc, stiffness_scale, a);
   const double h2 = md.h * md.h;
   double* o = cell + static_cast<size_t>(kl) * CELL_STRIDE * md.ncells + c;
+#if MODE != 0
+  // F is constant per system: the matrix entries and the det-weighted basis integrals are the same in
+  // every cell and the gather reads them from cell 0 (GatherArgs::uniform_stiffness)
+  if (c == 0) {
+#pragma unroll
+    for (int e = 0; e < 10; ++e) o[static_cast<size_t>(e) * md.ncells] = a[e];
+#pragma unroll
+    for (int e = 14; e < CELL_STRIDE; ++e) o[static_cast<size_t>(e) * md.ncells] = acc[e] * h2;
+  }
+#pragma unroll
+  for (int e = 10; e < 14; ++e) o[static_cast<size_t>(e) * md.ncells] = acc[e] * h2;
+#else
 #pragma unroll
   for (int e = 0; e < 10; ++e) o[static_cast<size_t>(e) * md.ncells] = a[e];
 #pragma unroll
   for (int e = 10; e < CELL_STRIDE; ++e) o[static_cast<size_t>(e) * md.ncells] = acc[e] * h2;
+#endif
   if (bad) *error_flag = 1;
 }
 )";

@@ -65,12 +65,17 @@ int upload_constant_tables(int q, const double* qtab, const double* qsum);
 int launch_face_moments(cudaStream_t s, const VmProgram& prog, int side, MeshDims md, Tables tb, const double* q1d_pt,
                         const double* q1d_wt, int k0, int nk, int has_map, double* face);
 
+int launch_face_moments_all(cudaStream_t s, const VmProgram* const prog[4], MeshDims md, Tables tb,
+                            const double* q1d_pt, const double* q1d_wt, int k0, int nk, int has_map, double* face);
+
 // K1 gather: cell (and face) arrays -> stencil diagonals + load vectors of systems [k0,k0+nk).
 struct GatherArgs {
   MeshDims md;
   int problem;
   int k0, nk;
   const double* cell;   // chunk-local
+  int uniform_stiffness;  // 1: F does not depend on y, so the 10 matrix entries and the 4 det-weighted basis
+                          // integrals are the same in every cell of a system: they are read from cell 0 only
   const double* face;   // chunk-local or null
   double robin_left, robin_right;  // kappa_2, kappa_4 (bio)
   double* diag;         // [N][NDIAG][ld]

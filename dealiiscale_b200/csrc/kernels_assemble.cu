@@ -124,6 +124,20 @@ __global__ void __launch_bounds__(TB) k_face_moments(const __grid_constant__ VmP
   body_face_moments(prog, side, md, tb, q1d_pt, q1d_wt, k0, nk, has_map, face,
                     static_cast<long long>(blockIdx.x) * TB + threadIdx.x, R + threadIdx.x, TB);
 }
+// all four sides in one launch (blockIdx.y = side): the four launches were latency-bound
+__global__ void __launch_bounds__(TB) k_face_moments4(const __grid_constant__ VmProgram p0,
+                                                       const __grid_constant__ VmProgram p1,
+                                                       const __grid_constant__ VmProgram p2,
+                                                       const __grid_constant__ VmProgram p3, MeshDims md, Tables tb,
+                                                       const double* __restrict__ q1d_pt,
+                                                       const double* __restrict__ q1d_wt, int k0, int nk, int has_map,
+                                                       double* __restrict__ face) {
+  extern __shared__ double R[];
+  const int side = blockIdx.y;
+  const VmProgram& prog = side == 0 ? p0 : side == 1 ? p1 : side == 2 ? p2 : p3;
+  body_face_moments(prog, side, md, tb, q1d_pt, q1d_wt, k0, nk, has_map, face,
+                    static_cast<long long>(blockIdx.x) * TB + threadIdx.x, R + threadIdx.x, TB);
+}
 __global__ void __launch_bounds__(TB) k_gather(GatherArgs a) {
   body_gather(a, static_cast<long long>(blockIdx.x) * TB + threadIdx.x);
 }
@@ -200,6 +214,22 @@ int launch_face_moments(cudaStream_t s, const VmProgram& prog, int side, MeshDim
   if (nk == 0) return 0;
   k_face_moments<<<blocks_for(static_cast<long long>(nk) * md.nc), TB, vm_smem(prog, TB), s>>>(
       prog, side, md, tb, q1d_pt, q1d_wt, k0, nk, has_map, face);
+  return 1;
+}
+
+int launch_face_moments_all(cudaStream_t s, const VmProgram* const prog[4], MeshDims md, Tables tb,
+                            const double* q1d_pt, const double* q1d_wt, int k0, int nk, int has_map, double* face) {
+  if (nk == 0) return 0;
+  size_t sm = 0;
+  for (int i = 0; i < 4; ++i) sm = vm_smem(*prog[i], TB) > sm ? vm_smem(*prog[i], TB) : sm;
+  if (sm > 48 * 1024) {  // very large programs: one launch per side
+    int n = 0;
+    for (int i = 0; i < 4; ++i) n += launch_face_moments(s, *prog[i], i, md, tb, q1d_pt, q1d_wt, k0, nk, has_map, face);
+    return n;
+  }
+  dim3 grid(blocks_for(static_cast<long long>(nk) * md.nc), 4);
+  k_face_moments4<<<grid, TB, sm, s>>>(*prog[0], *prog[1], *prog[2], *prog[3], md, tb, q1d_pt, q1d_wt, k0, nk, has_map,
+                                        face);
   return 1;
 }
 

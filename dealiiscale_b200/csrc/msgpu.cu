@@ -468,14 +468,17 @@ int msgpu_assemble(msgpu_ctx* ctx) {
                                        ctx->d_qtab + static_cast<size_t>(md.q) * md.q * QTAB_STRIDE, k0, nk, d2,
                                        ctx->d_cell, ctx->d_flags + FLAG_JACOBIAN);
       ctx->launches += launched;
-      if (prob == MSGPU_BIO)
-        for (int s = 0; s < 4; ++s)
-          ctx->launches += launch_face_moments(ctx->stream, ps.point_program(ctx->pp.prog_face[s]), s, md, tb, ctx->d_q1pt,
-                                               ctx->d_q1wt, k0, nk, ctx->pp.has_map, ctx->d_face);
+      if (prob == MSGPU_BIO) {
+        const VmProgram* faces[4];
+        for (int s = 0; s < 4; ++s) faces[s] = &ps.point_program(ctx->pp.prog_face[s]);
+        ctx->launches += launch_face_moments_all(ctx->stream, faces, md, tb, ctx->d_q1pt, ctx->d_q1wt, k0, nk,
+                                                 ctx->pp.has_map, ctx->d_face);
+      }
     }
     {
       PhaseTimer pt(ctx, PH_GATHER);
-      GatherArgs g;
+      GatherArgs g{};
+      g.uniform_stiffness = (!ctx->pp.has_map || !ctx->pp.jac_depends_on_y) ? 1 : 0;
       g.md = md;
       g.problem = prob;
       g.k0 = k0;

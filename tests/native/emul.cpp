@@ -318,7 +318,8 @@ int emul_assemble(void* h, const double* u, const double* w) {
         body_face_moments(fp, s, md, tb, e->q1pt.data(), e->q1wt.data(), 0, N, e->pp.has_map, e->face.data(), g,
                           e->regs(fp), TBE);
     }
-  GatherArgs ga;
+  GatherArgs ga{};
+  ga.uniform_stiffness = (!e->pp.has_map || !e->pp.jac_depends_on_y) ? 1 : 0;
   ga.md = md;
   ga.problem = prob;
   ga.k0 = 0;
