@@ -114,6 +114,7 @@ struct CgArgs {
   const double* b;          // [N][n]
   double* x;                // [N][n] in: start vector, out: solution
   double tol;
+  double tol2;              // set by launch_cg: largest t with sqrt(t) <= tol
   int max_it;
   int precond;
   int* iters;               // [N]

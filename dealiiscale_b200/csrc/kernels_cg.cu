@@ -21,12 +21,16 @@
 // warps, so results are bit-reproducible from run to run and independent of the SM.
 #include <cooperative_groups.h>
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 
 #include "kernels.h"
 
+#ifndef MSGPU_FAST_SCALARS
+#define MSGPU_FAST_SCALARS 1
+#endif
 namespace msgpu {
 
 namespace {
@@ -521,6 +525,7 @@ template <int BT, int K, bool JACOBI>
 __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
   constexpr int CW = (512 / (BT / 128)) & ~1;  // TMEM columns per warp
   constexpr int NACC = K >= 12 ? 4 : 1;        // K = 9 stays bit-identical to k_cg_strip
+  constexpr bool FAST = MSGPU_FAST_SCALARS;
   static_assert(BT % 128 == 0 && 14 * K + 2 <= CW, "strip must fit the TMEM columns of a thread");
   extern __shared__ __align__(16) double sm[];
   __shared__ int s_k;
@@ -684,6 +689,7 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
         }
         gh = res * res;
       }
+      double rgh = FAST ? 1.0 / gh : 0.0;
       for (;;) {
         ++it;
         __syncthreads();
@@ -696,12 +702,24 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
           gg[j] += alpha * hh[j];
         }
         part = strip_dot<K, NACC>([&](int j) { return gg[j] * gg[j]; });
-        res = sqrt(block_sum_tree<BT>(part, red + 32));
-        if (res <= a.tol) {
-          ok = true;
-          break;
+        const double s2 = block_sum_tree<BT>(part, red + 32);
+        double gh_new;
+        if (FAST) {
+          res = s2;
+          gh_new = s2;
+          if (s2 <= a.tol2) {
+            ok = true;
+            break;
+          }
+        } else {
+          res = sqrt(s2);
+          gh_new = res * res;
+          if (res <= a.tol) {
+            ok = true;
+            break;
+          }
         }
-        if (it >= a.max_it || res != res) break;
+        if (it >= a.max_it || s2 != s2) break;
         double beta = gh;
         if (JACOBI) {
           part = 0.0;
@@ -718,8 +736,9 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
             if (j < nlive) dv[r0 + j] = dl[j];
           }
         } else {
-          gh = res * res;
-          beta = gh / beta;
+          beta = FAST ? gh_new * rgh : gh_new / beta;
+          gh = gh_new;
+          if (FAST) rgh = 1.0 / gh;
 #pragma unroll
           for (int j = 0; j < K; ++j) {
             dl[j] = beta * dl[j] - gg[j];
@@ -728,6 +747,7 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
         }
       }
     }
+    if (FAST && it > 0) res = sqrt(res);
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < K; ++j)
@@ -1244,8 +1264,18 @@ size_t g_workspace_bytes = 0;
 
 }  // namespace
 
-int launch_cg(cudaStream_t s, const CgArgs& a, int num_sms, int* variant) {
-  if (a.N == 0) return 0;
+static double squared_threshold(double tol) {
+  if (!(tol > 0.0)) return tol == 0.0 ? 0.0 : -1.0;
+  double t = tol * tol;
+  while (std::sqrt(std::nextafter(t, INFINITY)) <= tol) t = std::nextafter(t, INFINITY);
+  while (std::sqrt(t) > tol) t = std::nextafter(t, 0.0);
+  return t;
+}
+
+int launch_cg(cudaStream_t s, const CgArgs& a_in, int num_sms, int* variant) {
+  if (a_in.N == 0) return 0;
+  CgArgs a = a_in;
+  a.tol2 = squared_threshold(a.tol);
   cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
   cudaMemsetAsync(a.fail_flag, 0, sizeof(int), s);
   const int n = a.md.n;
