@@ -9,5 +9,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-fil
 echo "launch list rc=$?"
 CMD2="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --macro-ref 4"
 $CMD2 > gpurun_out/ncu_plain2.json 2> gpurun_out/ncu_plain2.err && \
-ncu --set full --clock-control none --import-source on -k regex:'k_cg_strip|k_cg_resident|k_cell_moments' -s 6 -c 2 -o gpurun_out/prof_$TAG $CMD2 > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_cg_strip|k_cg_resident|k_cell_moments|k_gather' -s 6 -c 3 -o gpurun_out/prof_$TAG $CMD2 > gpurun_out/ncu_full.log 2>&1
 echo "full rc=$?"
