@@ -195,7 +195,11 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     micro_cells = 2 ** args.micro_ref
     prm_path = os.path.join(ROOT, "input", args.prm)
-    sample = args.cpu_sample or 128 * threads
+    # bounded sample per step: the whole --steps/--warmup run should end within ~3 minutes
+    probe = cpu_baseline(prm_path, 2 ** args.macro_ref, micro_cells, 8 * threads, threads)
+    systems_per_s = 8 * threads / max(probe["seconds"], 1e-3)
+    budget = 150.0 / (args.steps + 0.5 * args.warmup + 1e-9)
+    sample = args.cpu_sample or int(min(128 * threads, max(threads, systems_per_s * budget)))
     vals = []
     for _ in range(args.warmup):
         cpu_baseline(prm_path, 2 ** args.macro_ref, micro_cells, max(1, sample // 2), threads)
