@@ -57,7 +57,8 @@ struct msgpu_ctx {
   msgpu::ProblemPrograms pp;
 
   // run-time specialised kernels (jit.h); jit_log keeps why a specialisation was not possible
-  msgpu::JitKernel jit_moments;
+  msgpu::JitKernel jit_moments, jit_errors;
+  int jit_errors_ready = 0;
   int jit_kernels = 0;
   std::string jit_log;
 

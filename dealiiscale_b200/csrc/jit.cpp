@@ -145,4 +145,14 @@ int launch_cell_moments_jit(cudaStream_t s, const JitKernel& jk, MeshDims md, Ta
   return e == cudaSuccess ? 1 : -1;
 }
 
+int launch_cell_errors_jit(cudaStream_t s, const JitKernel& jk, MeshDims md, const double* slots, int n_slots, int qe,
+                           const double* pt, const double* wt, const double* x, int N, double fd, double* cellred) {
+  if (N == 0) return 0;
+  const long long work = static_cast<long long>(N) * md.ncells;
+  void* args[] = {&md, &slots, &n_slots, &qe, &pt, &wt, &x, &N, &fd, &cellred};
+  const cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(jk.kernel),
+                                         dim3(static_cast<unsigned>((work + 127) / 128)), dim3(128), args, 0, s);
+  return e == cudaSuccess ? 1 : -1;
+}
+
 }  // namespace msgpu

@@ -40,6 +40,9 @@ std::string vm_to_cuda(const VmProgram& prog, const std::string& name, int W);
 std::string cell_moments_source(const MomentPrograms& mp, int q, const double* qtab, const double* qsum,
                                 bool* unrolled_rows);
 
+// Source of the per-cell error kernel (exact solution program, MODE_POINTS) — mirrors body_cell_errors.
+std::string cell_errors_source(const VmProgram& prog);
+
 // Compiles `src` (entry point `kernel_name`, extern "C") for sm_100a and loads it on the current
 // device.  Identical sources are compiled once per process.  Returns 0 on success; otherwise *log
 // holds the NVRTC / loader message.
@@ -47,5 +50,8 @@ int jit_compile(const std::string& src, const char* kernel_name, JitKernel* out,
 
 int launch_cell_moments_jit(cudaStream_t s, const JitKernel& jk, MeshDims md, Tables tb, int k0, int nk,
                             double stiffness_scale, double* cell, int* error_flag);
+
+int launch_cell_errors_jit(cudaStream_t s, const JitKernel& jk, MeshDims md, const double* slots, int n_slots, int qe,
+                           const double* pt, const double* wt, const double* x, int N, double fd, double* cellred);
 
 }  // namespace msgpu

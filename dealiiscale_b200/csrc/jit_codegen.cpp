@@ -311,4 +311,68 @@ extern "C" __global__ void __launch_bounds__(128) k_cell_moments_jit(MeshDims md
   return o.str();
 }
 
+// The kernel text mirrors body_cell_errors (extra_bodies.cuh); the five evaluations of the exact
+// solution per quadrature point (value + central differences) run as five lanes of one program.
+std::string cell_errors_source(const VmProgram& prog) {
+  const std::string fn = vm_to_cuda(prog, "prog_exact", 5);
+  if (fn.empty()) return std::string();
+  std::ostringstream o;
+  o << "// generated by libmsgpu (jit_codegen.cpp): per-cell error integrals\n";
+  o << "#define NREG " << (prog.n_regs < 2 ? 2 : prog.n_regs) << "\n#define OUT0 " << prog.out0 << "\n";
+  o << R"(
+struct MeshDims { int nc, m, n, ld, ncells, q, P; double h; };
+__device__ __forceinline__ int vm_round(double v) { return static_cast<int>(v + ((v >= 0.0) ? 0.5 : -0.5)); }
+)";
+  // the generated function declares R[n_regs][5]; make the declared size match NREG
+  std::string f = fn;
+  const std::string decl = "double (&R)[" + std::to_string(prog.n_regs < 1 ? 1 : prog.n_regs) + "][5]";
+  const size_t pos = f.find(decl);
+  if (pos == std::string::npos) return std::string();
+  f.replace(pos, decl.size(), "double (&R)[NREG][5]");
+  o << f << "\n";
+  o << R"(
+extern "C" __global__ void __launch_bounds__(128) k_cell_errors_jit(MeshDims md, const double* __restrict__ slots,
+                                                                     int n_slots, int qe,
+                                                                     const double* __restrict__ pt,
+                                                                     const double* __restrict__ wt,
+                                                                     const double* __restrict__ x, int N, double fd,
+                                                                     double* __restrict__ out) {
+  const long long gtid = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
+  if (gtid >= static_cast<long long>(N) * md.ncells) return;
+  const int k = static_cast<int>(gtid / md.ncells), c = static_cast<int>(gtid % md.ncells);
+  const int cx = c / md.nc, cy = c % md.nc;
+  const double* U = slots + static_cast<size_t>(k) * n_slots;
+  const double* xk = x + static_cast<size_t>(k) * md.n;
+  const double v0 = xk[cx * md.m + cy], v1 = xk[(cx + 1) * md.m + cy];
+  const double v2 = xk[cx * md.m + cy + 1], v3 = xk[(cx + 1) * md.m + cy + 1];
+  const double ox = -1.0 + cx * md.h, oy = -1.0 + cy * md.h;
+  double l2 = 0.0, semi = 0.0;
+  for (int qy = 0; qy < qe; ++qy)
+    for (int qx = 0; qx < qe; ++qx) {
+      const double xi = pt[qx], eta = pt[qy];
+      const double y0 = ox + md.h * xi, y1 = oy + md.h * eta;
+      const double jxw = wt[qx] * wt[qy] * md.h * md.h;
+      const double vh = v0 * ((1 - xi) * (1 - eta)) + v1 * (xi * (1 - eta)) + v2 * ((1 - xi) * eta) + v3 * (xi * eta);
+      const double gx = (-(1 - eta) * v0 + (1 - eta) * v1 - eta * v2 + eta * v3) / md.h;
+      const double gy = (-(1 - xi) * v0 - xi * v1 + (1 - xi) * v2 + xi * v3) / md.h;
+      double R[NREG][5];
+      R[0][0] = y0;      R[1][0] = y1;
+      R[0][1] = y0 + fd; R[1][1] = y1;
+      R[0][2] = y0 - fd; R[1][2] = y1;
+      R[0][3] = y0;      R[1][3] = y1 + fd;
+      R[0][4] = y0;      R[1][4] = y1 - fd;
+      prog_exact(U, nullptr, 0, nullptr, 0, R);
+      const double s = R[OUT0][0];
+      const double sx = (R[OUT0][1] - R[OUT0][2]) / (2 * fd);
+      const double sy = (R[OUT0][3] - R[OUT0][4]) / (2 * fd);
+      l2 += (vh - s) * (vh - s) * jxw;
+      semi += ((gx - sx) * (gx - sx) + (gy - sy) * (gy - sy)) * jxw;
+    }
+  out[(static_cast<size_t>(k) * 2 + 0) * md.ncells + c] = l2;
+  out[(static_cast<size_t>(k) * 2 + 1) * md.ncells + c] = semi;
+}
+)";
+  return o.str();
+}
+
 }  // namespace msgpu

@@ -88,6 +88,11 @@ int launch_cell_errors(cudaStream_t s, const VmProgram& prog, MeshDims md, const
   return 2;
 }
 
+static int launch_reduce_cells(cudaStream_t s, const double* cellred, int N, int ncells, double* out2) {
+  k_reduce_cells<<<blocks(static_cast<long long>(2) * N * 32), TBX, 0, s>>>(cellred, N, ncells, out2);
+  return 1;
+}
+
 int launch_cell_residuals(cudaStream_t s, MeshDims md, const double* x, const double* xold, int N, double* cellred,
                           double* out2) {
   const long long work = static_cast<long long>(N) * md.ncells;
@@ -131,9 +136,31 @@ int compute_errors(msgpu_ctx* ctx, double* l2, double* h1) {
   const MeshDims& md = ctx->md;
   const int N = ctx->N;
   if ((rc = ensure(ctx, &ctx->d_cellred, static_cast<size_t>(N) * 2 * md.ncells))) return rc;
-  ctx->launches += launch_cell_errors(ctx->stream, ctx->pp.ps.point_program(ctx->pp.prog_err), md, ctx->d_slots,
-                                      ctx->pp.ps.n_slots(), ctx->eq_degree, ctx->d_eq_pt, ctx->d_eq_wt, ctx->d_x, N,
-                                      1e-8, ctx->d_cellred, ctx->d_err);
+  // the exact-solution program specialised at first use (jit.h); the interpreter kernel is the fallback
+  const VmProgram& exact = ctx->pp.ps.point_program(ctx->pp.prog_err);
+  if (ctx->jit_errors_ready == 0) {
+    const char* jit_env = std::getenv("MSGPU_JIT");
+    ctx->jit_errors_ready = -1;
+    if (!(jit_env && jit_env[0] == '0')) {
+      const std::string src = cell_errors_source(exact);
+      std::string log;
+      if (!src.empty() && jit_compile(src, "k_cell_errors_jit", &ctx->jit_errors, &log) == 0) {
+        ctx->jit_errors_ready = 1;
+        ctx->jit_kernels += 1;
+      } else if (ctx->jit_log.empty()) {
+        ctx->jit_log = src.empty() ? "the exact-solution program uses an instruction the code generator does not lower" : log;
+      }
+    }
+  }
+  int launched = -1;
+  if (ctx->jit_errors_ready == 1)
+    launched = launch_cell_errors_jit(ctx->stream, ctx->jit_errors, md, ctx->d_slots, ctx->pp.ps.n_slots(),
+                                      ctx->eq_degree, ctx->d_eq_pt, ctx->d_eq_wt, ctx->d_x, N, 1e-8, ctx->d_cellred);
+  if (launched > 0)
+    ctx->launches += launched + launch_reduce_cells(ctx->stream, ctx->d_cellred, N, md.ncells, ctx->d_err);
+  else
+    ctx->launches += launch_cell_errors(ctx->stream, exact, md, ctx->d_slots, ctx->pp.ps.n_slots(), ctx->eq_degree,
+                                        ctx->d_eq_pt, ctx->d_eq_wt, ctx->d_x, N, 1e-8, ctx->d_cellred, ctx->d_err);
   CKX(cudaGetLastError());
   std::vector<double> sums(2 * static_cast<size_t>(N));
   CKX(cudaMemcpyAsync(sums.data(), ctx->d_err, sizeof(double) * sums.size(), cudaMemcpyDeviceToHost, ctx->stream));

@@ -312,6 +312,7 @@ int msgpu_setup(msgpu_ctx* ctx) {
   // Specialise the cell-moment kernel for this problem's expressions (elliptic and bio assemble
   // every cycle).  Any failure leaves the interpreter kernels in charge and is kept in jit_log.
   ctx->jit_kernels = 0;
+  ctx->jit_errors_ready = 0;
   ctx->jit_log.clear();
   {
     const char* jit_env = std::getenv("MSGPU_JIT");

@@ -2,6 +2,7 @@
 // Host mirror of reference src/bio-multiscale/{macro,manager}.{h,cpp} and manufactured.cpp.
 #pragma once
 #include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <fstream>
 
@@ -261,10 +262,31 @@ class Manager {
   int cycle = 0;
   std::string ct_file_name;
   void fixed_point_iterate() {  // manager.cpp:65-68
+    const bool timing = std::getenv("MSGPU_DRIVER_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     macro_solver.assemble_and_solve();
+    const auto t1 = std::chrono::steady_clock::now();
     micro_solver.assemble_and_solve_all();
+    const auto t2 = std::chrono::steady_clock::now();
+    if (timing) {
+      long long its = 0;
+      for (int v : micro_solver.iterations) its += v;
+      std::printf("[timing] macro %.2f ms, micro %.2f ms (mean CG steps %.1f)\n",
+                  std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                  std::chrono::duration<double, std::milli>(t2 - t1).count(),
+                  micro_solver.iterations.empty() ? 0.0 : double(its) / micro_solver.iterations.size());
+    }
   }
   void check_fixed_point_reached(bool& reached) {  // manager.cpp:70-109
+    const auto t_check = std::chrono::steady_clock::now();
+    struct Report {
+      std::chrono::steady_clock::time_point t0;
+      ~Report() {
+        if (std::getenv("MSGPU_DRIVER_TIMING"))
+          std::printf("[timing] stop test %.2f ms\n",
+                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+      }
+    } report{t_check};
     CycleRecord r;
     r.cycle = cycle;
     if (functions.data.params.get_bool("has_solution")) {

@@ -7,6 +7,7 @@
 // Macro functions of (x0,x1[,t]) are compiled with the same expression compiler as the micro
 // functions and evaluated by running the VM on the host (expr_vm.cuh is host/device code).
 #pragma once
+#include <thread>
 #include <cstdlib>
 #include <algorithm>
 #include <array>
@@ -34,13 +35,20 @@ class MacroFunction {
     slots_.assign(std::max(1, set_.n_slots()), 0.0);
   }
   void set_time(double t) { time_ = t; }
-  double value(double x0, double x1) const {
+  double value(double x0, double x1) const {  // thread-safe: all scratch is local
     double regs[16] = {x0, x1, time_};
+    double small[32];
+    std::vector<double> big;
+    double* slots = small;
+    if (slots_.size() > 32) {
+      big.assign(slots_.size(), 0.0);
+      slots = big.data();
+    }
     msgpu::VmIo io{};
     io.R = regs;
     io.r_stride = 1;
-    io.OUT = slots_.data();
-    io.U = slots_.data();
+    io.OUT = slots;
+    io.U = slots;
     io.out_stride = 1;
     if (set_.n_slots() > 0) msgpu::vm_run(set_.slot_program(), 0, io);
     const msgpu::VmProgram& p = set_.point_program(prog_);
@@ -286,8 +294,12 @@ inline double nodal_l2_norm(const MacroMesh& mesh, const std::vector<double>& va
 inline void field_errors(const MacroMesh& mesh, const std::vector<double>& u, const MacroFunction& exact, int q,
                          double& l2, double& h1) {
   Quadrature Q(q);
-  double sl2 = 0, sh1 = 0;
-  for (size_t c = 0; c < mesh.cell_dofs.size(); ++c) {
+  // cells are independent (5 expression evaluations per point): host threads over cell ranges, per-cell
+  // sums added in cell order afterwards, so the result does not depend on the thread count
+  const size_t n_cells = mesh.cell_dofs.size();
+  std::vector<double> cell_l2(n_cells), cell_h1(n_cells);
+  auto work = [&](size_t c0, size_t c1) {
+  for (size_t c = c0; c < c1; ++c) {
     const double ox = -1.0 + mesh.cell_cx[c] * mesh.h, oy = -1.0 + mesh.cell_cy[c] * mesh.h;
     double cl2 = 0, ch1 = 0;
     for (int j = 0; j < q; ++j)
@@ -310,8 +322,27 @@ inline void field_errors(const MacroMesh& mesh, const std::vector<double>& u, co
         cl2 += d * d * jxw;
         ch1 += ((gx - eg[0]) * (gx - eg[0]) + (gy - eg[1]) * (gy - eg[1])) * jxw;
       }
-    sl2 += cl2;
-    sh1 += ch1;
+    cell_l2[c] = cl2;
+    cell_h1[c] = ch1;
+  }
+  };
+  unsigned int T = std::thread::hardware_concurrency();
+  if (T > 32) T = 32;
+  if (T < 2 || n_cells < 256) {
+    work(0, n_cells);
+  } else {
+    std::vector<std::thread> pool;
+    const size_t chunk = (n_cells + T - 1) / T;
+    for (unsigned int t = 0; t < T; ++t) {
+      const size_t c0 = t * chunk, c1 = std::min(n_cells, c0 + chunk);
+      if (c0 < c1) pool.emplace_back(work, c0, c1);
+    }
+    for (auto& th : pool) th.join();
+  }
+  double sl2 = 0, sh1 = 0;
+  for (size_t c = 0; c < n_cells; ++c) {
+    sl2 += cell_l2[c];
+    sh1 += cell_h1[c];
   }
   l2 = std::sqrt(sl2);
   h1 = std::sqrt(sh1);

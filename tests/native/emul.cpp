@@ -509,6 +509,34 @@ int emul_coupling(void* h, double* c0, double* c1) {
 }
 
 
+// Text of the run-time specialised error kernel (exact-solution program), as emul_jit_source.
+int emul_jit_errors_source(void* h, char* buf, int len) {
+  Emul* e = static_cast<Emul*>(h);
+  if (e->pp.prog_err < 0) return 0;
+  const std::string src = cell_errors_source(e->pp.ps.point_program(e->pp.prog_err));
+  if (src.empty()) return 0;
+  if (buf && len > 0) {
+    std::strncpy(buf, src.c_str(), len - 1);
+    buf[len - 1] = 0;
+  }
+  return static_cast<int>(src.size()) + 1;
+}
+// Per-cell error integrals of the interpreter body: out[(k*2 + {0,1})*ncells + c].
+int emul_cell_errors(void* h, double* out) {
+  Emul* e = static_cast<Emul*>(h);
+  if (e->pp.prog_err < 0) return 1;
+  const MeshDims& md = e->md;
+  const int qe = e->problem == PF_PARABOLIC ? 3 : md.q;
+  std::vector<double> pt, wt;
+  gauss_legendre_unit(qe, pt, wt);
+  const VmProgram& prog = e->pp.ps.point_program(e->pp.prog_err);
+  for (long long g = 0; g < static_cast<long long>(e->N) * md.ncells; ++g)
+    body_cell_errors(prog, md, e->slots.data(), e->pp.ps.n_slots(), qe, pt.data(), wt.data(), e->x.data(), e->N, 1e-8,
+                     out, g, e->regs(prog), TBE);
+  return 0;
+}
+const double* emul_solution_pointer(void* h) { return static_cast<Emul*>(h)->x.data(); }
+
 // ---- errors / residuals (same bodies as kernels_extra.cu, sequential) ---------------------------
 int emul_errors(void* h, double* l2, double* h1) {
   Emul* e = static_cast<Emul*>(h);

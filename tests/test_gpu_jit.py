@@ -86,3 +86,33 @@ def test_jit_can_be_switched_off():
         ms.close()
     finally:
         os.environ.pop("MSGPU_JIT", None)
+
+
+@pytest.mark.parametrize("problem,prm,cells", [("elliptic", "elliptic_non_linear.prm", 8), ("bio", "linear.prm", 8)])
+def test_specialised_error_kernel_matches_interpreter(problem, prm, cells):
+    from dealiiscale_b200 import capi
+    from dealiiscale_b200.micro import MicroSolver
+    from dealiiscale_b200.prm import BioData, EllipticData
+
+    g = np.linspace(-0.9, 0.8, 3)
+    xy = np.array([(a, b) for b in g for a in g])
+    u, w = 1.0 + 0.5 * xy[:, 0], 0.25 - xy[:, 1]
+    out = {}
+    for jit in (False, True):
+        os.environ["MSGPU_JIT"] = "1" if jit else "0"
+        try:
+            data = (BioData if problem == "bio" else EllipticData)(os.path.join(INPUT, prm))
+            ms = MicroSolver(capi.BIO if problem == "bio" else capi.ELLIPTIC, data, cells)
+            ms.set_grid_locations(xy)
+            ms.setup()
+            ms.set_macro_solution(u, w if problem == "bio" else None)
+            ms.run()
+            out[jit] = ms.grid_errors()
+            assert ms.stats()["jit_kernels"] == (2 if jit else 0), ms.jit_log()
+            ms.close()
+        finally:
+            os.environ.pop("MSGPU_JIT", None)
+    # same expression values (one IEEE operation per bytecode instruction in both); the surrounding
+    # arithmetic may be contracted differently by nvcc and NVRTC
+    np.testing.assert_allclose(out[True][0], out[False][0], rtol=1e-9)
+    np.testing.assert_allclose(out[True][1], out[False][1], rtol=1e-6)

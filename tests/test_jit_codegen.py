@@ -155,3 +155,87 @@ def test_nvrtc_accepts_the_generated_kernel(problem, prm):
     assert size.value > 1000
     nv.nvrtcDestroyProgram(C.byref(prog))
     e.close()
+
+
+ERR_DRIVER = r"""
+extern "C" void host_run_errors(const int* d, double h, const double* slots, int qe, const double* pt, const double* wt,
+                                const double* x, int N, double fd, double* out) {
+  MeshDims md{d[3], d[4], d[5], d[6], d[7], d[8], d[9], h};
+  const long long work = static_cast<long long>(N) * md.ncells;
+  for (long long t = 0; t < work; ++t) {
+    blockIdx.x = static_cast<unsigned>(t / 128);
+    threadIdx.x = static_cast<unsigned>(t % 128);
+    k_cell_errors_jit(md, slots, d[0], qe, pt, wt, x, N, fd, out);
+  }
+}
+"""
+
+
+def _errors_source(e):
+    e.lib.emul_jit_errors_source.restype = C.c_int
+    e.lib.emul_jit_errors_source.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    n = e.lib.emul_jit_errors_source(e.h, None, 0)
+    assert n > 0
+    buf = C.create_string_buffer(n)
+    e.lib.emul_jit_errors_source(e.h, buf, n)
+    return buf.value.decode()
+
+
+@pytest.mark.parametrize("problem,prm,nc", [("elliptic", "elliptic_non_linear.prm", 4), ("bio", "linear.prm", 3)])
+def test_generated_error_kernel_equals_interpreter_on_the_host(problem, prm, nc, tmp_path):
+    e, xy = _emul(problem, prm, nc, 12)
+    src = _errors_source(e)
+    cpp = tmp_path / "e.cpp"
+    cpp.write_text(SHIM + src + ERR_DRIVER)
+    so = tmp_path / "e.so"
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                           "-Wno-unknown-pragmas", "-o", str(so), str(cpp)])
+    lib = C.CDLL(str(so))
+    N, ncells = len(xy), nc * nc
+    e.assemble(1.0 + xy[:, 0], 0.5 - xy[:, 1])
+    e.solve(1e-12, 1000)
+    want = np.zeros(N * 2 * ncells)
+    e.lib.emul_cell_errors.argtypes = [C.c_void_p, C.c_void_p]
+    assert e.lib.emul_cell_errors(e.h, dptr(want)) == 0
+    slots, t0, t1 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    dims = (C.c_int * 10)()
+    e.lib.emul_table_pointers.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 3 + [C.POINTER(C.c_int)]
+    e.lib.emul_table_pointers(e.h, C.byref(slots), C.byref(t0), C.byref(t1), dims)
+    e.lib.emul_mesh_h.restype = C.c_double
+    e.lib.emul_mesh_h.argtypes = [C.c_void_p]
+    e.lib.emul_solution_pointer.restype = C.c_void_p
+    e.lib.emul_solution_pointer.argtypes = [C.c_void_p]
+    from helpers import load_oracle
+    pt, wt = np.zeros(12), np.zeros(12)
+    load_oracle().orc_gauss01(12, dptr(pt), dptr(wt))
+    got = np.zeros_like(want)
+    lib.host_run_errors.argtypes = [C.POINTER(C.c_int), C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+    lib.host_run_errors(dims, e.lib.emul_mesh_h(e.h), slots, 12, dptr(pt), dptr(wt),
+                        C.c_void_p(e.lib.emul_solution_pointer(e.h)), N, 1e-8, dptr(got))
+    assert np.abs(want).max() > 0
+    # the quadrature nodes come from two Gauss-Legendre routines that agree to the last ulp or two; the
+    # central differences (step 1e-8) amplify that, so the H1 part is compared to 1e-6
+    got, want = got.reshape(N, 2, ncells), want.reshape(N, 2, ncells)
+    np.testing.assert_allclose(got[:, 0], want[:, 0], rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(got[:, 1], want[:, 1], rtol=1e-5, atol=1e-300)
+    e.close()
+
+
+def test_nvrtc_accepts_the_generated_error_kernel():
+    nv = _nvrtc()
+    if nv is None:
+        pytest.skip("NVRTC not installed")
+    e, _ = _emul("elliptic", "elliptic_non_linear.prm", 4, 12)
+    src = _errors_source(e)
+    prog = C.c_void_p()
+    assert nv.nvrtcCreateProgram(C.byref(prog), src.encode(), b"msgpu_jit_err.cu", 0, None, None) == 0
+    opts = [b"--gpu-architecture=sm_100a", b"--std=c++17", b"-lineinfo"]
+    rc = nv.nvrtcCompileProgram(prog, len(opts), (C.c_char_p * len(opts))(*opts))
+    size = C.c_size_t()
+    nv.nvrtcGetProgramLogSize(prog, C.byref(size))
+    log = C.create_string_buffer(size.value)
+    nv.nvrtcGetProgramLog(prog, log)
+    assert rc == 0, log.value.decode()
+    nv.nvrtcDestroyProgram(C.byref(prog))
+    e.close()
