@@ -239,3 +239,53 @@ def test_nvrtc_accepts_the_generated_error_kernel():
     assert rc == 0, log.value.decode()
     nv.nvrtcDestroyProgram(C.byref(prog))
     e.close()
+
+
+def _emul_with_rhs(expr, consts):
+    from helpers import ELLIPTIC, FN_BC, FN_JACOBIAN, FN_MAPPING, FN_RHS, FN_SOLUTION, MESH_REFINE_GLOBAL
+
+    e = Emul(ELLIPTIC, MESH_REFINE_GLOBAL, 2, 12)
+    e.set_function(FN_MAPPING, "0.9*y0 + 0.1*x0; 1.1*y1 - 0.05*x1", consts)
+    e.set_function(FN_JACOBIAN, "0.9; 0; 0; 1.1", consts)
+    e.set_function(FN_RHS, expr, consts)
+    e.set_function(FN_BC, "0", consts)
+    e.set_function(FN_SOLUTION, "0", consts)
+    xy = np.array([[-0.5, 0.25], [0.3, 0.7]])
+    e.setup(xy)
+    return e, xy
+
+
+def test_every_opcode_is_lowered_like_the_interpreter_executes_it(tmp_path):
+    """The expression list of test_expr_compile.py (all operators and functions of the grammar) as right-hand
+    sides: the generated straight-line code, run on the host, must reproduce the interpreter bit for bit."""
+    from test_expr_compile import CONSTS, EXPRS
+
+    for n, expr in enumerate(EXPRS):
+        e, xy = _emul_with_rhs(expr, CONSTS)
+        src = _source(e)
+        cpp = tmp_path / f"k{n}.cpp"
+        cpp.write_text(SHIM + src + DRIVER)
+        so = tmp_path / f"k{n}.so"
+        subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                               "-Wno-unknown-pragmas", "-o", str(so), str(cpp)])
+        lib = C.CDLL(str(so))
+        N, ncells = len(xy), 4
+        e.assemble(np.ones(N), np.ones(N))
+        want = np.zeros(N * 18 * ncells)
+        e.lib.emul_get_cell_scratch.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+        e.lib.emul_get_cell_scratch(e.h, dptr(want), want.size)
+        slots, t0, t1 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        dims = (C.c_int * 10)()
+        e.lib.emul_table_pointers.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 3 + [C.POINTER(C.c_int)]
+        e.lib.emul_table_pointers(e.h, C.byref(slots), C.byref(t0), C.byref(t1), dims)
+        e.lib.emul_mesh_h.restype = C.c_double
+        e.lib.emul_mesh_h.argtypes = [C.c_void_p]
+        got = np.zeros_like(want)
+        flag = C.c_int(0)
+        lib.host_run.argtypes = [C.POINTER(C.c_int), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                 C.c_double, C.c_void_p, C.POINTER(C.c_int)]
+        lib.host_run(dims, e.lib.emul_mesh_h(e.h), slots, t0, t1, N, 1.0, dptr(got), C.byref(flag))
+        got, want = got.reshape(N, 18, ncells), want.reshape(N, 18, ncells)
+        assert np.isfinite(want[:, 10:14]).all(), expr
+        assert np.array_equal(got[:, 10:14, :], want[:, 10:14, :]), expr
+        e.close()
