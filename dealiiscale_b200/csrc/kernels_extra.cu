@@ -193,34 +193,33 @@ int compute_residuals(msgpu_ctx* ctx, double* l2) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// parabolic: shared stencils built on the host (n entries, closed-form Q1 local matrices on a
-// square cell: what MatrixCreator::create_mass_matrix / create_laplace_matrix with QGauss(2)
-// integrate exactly, rho_solver.cpp:64-65)
-int parabolic_setup(msgpu_ctx* ctx) {
+// Batched L2 projection onto the Q1 space of every grid: VectorTools::project(dof_handler, constraints,
+// QGauss(qe), f, solutions[k]) for all k (rho_solver.cpp:80-83 for init_rho; micro.cpp:229-233,
+// bio micro.cpp:386-390, rho_solver.cpp:355-358 for the exact solution).  Load vectors by
+// k_cell_point_load + k_gather, then M x = load with the batched CG on the one shared mass stencil.
+// Overwrites the solutions AND the right-hand sides of the context.
+int project_into_solutions(msgpu_ctx* ctx, const VmProgram& prog, int qe, const char* what) {
   CKX(cudaSetDevice(ctx->device));
   const MeshDims& md = ctx->md;
   const int N = ctx->N;
   int rc;
-  if ((rc = ensure(ctx, &ctx->d_mass, static_cast<size_t>(NDIAG) * md.ld))) return rc;
-  if ((rc = ensure(ctx, &ctx->d_lumped, static_cast<size_t>(md.n)))) return rc;
-  std::vector<double> mass, sys, lumped;
-  build_stencils(md, 0.0, ctx->scalars[3], ctx->scalars[0], ctx->scalars[2], mass, sys, lumped);
-  CKX(cudaMemcpy(ctx->d_mass, mass.data(), sizeof(double) * mass.size(), cudaMemcpyHostToDevice));
-  CKX(cudaMemcpy(ctx->d_lumped, lumped.data(), sizeof(double) * lumped.size(), cudaMemcpyHostToDevice));
-  ctx->parabolic_dt = -1.0;
-  if (ctx->pp.prog_init < 0) return MSGPU_OK;  // start from zero
-  // rho_k^0 = L2 projection of init_rho(x_k, .) with QGauss(3) (rho_solver.cpp:78-83): M rho = load
+  if (!ctx->d_mass) {  // elliptic / bio contexts: the mass stencil is only needed here
+    if ((rc = ensure(ctx, &ctx->d_mass, static_cast<size_t>(NDIAG) * md.ld))) return rc;
+    std::vector<double> mass, sys, lumped;
+    build_stencils(md, 0.0, 0.0, 0.0, 0.0, mass, sys, lumped);
+    CKX(cudaMemcpy(ctx->d_mass, mass.data(), sizeof(double) * mass.size(), cudaMemcpyHostToDevice));
+  }
   std::vector<double> pt, wt;
-  gauss_legendre_unit(3, pt, wt);
+  gauss_legendre_unit(qe, pt, wt);
   double *d_pt = nullptr, *d_wt = nullptr;
-  CKX(cudaMalloc(reinterpret_cast<void**>(&d_pt), 3 * sizeof(double)));
-  CKX(cudaMalloc(reinterpret_cast<void**>(&d_wt), 3 * sizeof(double)));
-  CKX(cudaMemcpy(d_pt, pt.data(), 3 * sizeof(double), cudaMemcpyHostToDevice));
-  CKX(cudaMemcpy(d_wt, wt.data(), 3 * sizeof(double), cudaMemcpyHostToDevice));
+  CKX(cudaMalloc(reinterpret_cast<void**>(&d_pt), qe * sizeof(double)));
+  CKX(cudaMalloc(reinterpret_cast<void**>(&d_wt), qe * sizeof(double)));
+  CKX(cudaMemcpy(d_pt, pt.data(), qe * sizeof(double), cudaMemcpyHostToDevice));
+  CKX(cudaMemcpy(d_wt, wt.data(), qe * sizeof(double), cudaMemcpyHostToDevice));
   for (int k0 = 0; k0 < N; k0 += ctx->chunk) {
     const int nk = std::min(ctx->chunk, N - k0);
-    ctx->launches += launch_cell_point_load(ctx->stream, ctx->pp.ps.point_program(ctx->pp.prog_init), md, ctx->d_slots,
-                                            ctx->pp.ps.n_slots(), 3, d_pt, d_wt, k0, nk, ctx->d_cell);
+    ctx->launches += launch_cell_point_load(ctx->stream, prog, md, ctx->d_slots, ctx->pp.ps.n_slots(), qe, d_pt, d_wt,
+                                            k0, nk, ctx->d_cell);
     GatherArgs g{};
     g.md = md;
     g.problem = PF_PARABOLIC;
@@ -256,16 +255,56 @@ int parabolic_setup(msgpu_ctx* ctx) {
     return MSGPU_ERR_CUDA;
   }
   ctx->launches += l;
-  CKX(cudaMemcpyAsync(ctx->d_xold, ctx->d_x, sizeof(double) * N * md.n, cudaMemcpyDeviceToDevice, ctx->stream));
   int flags[4];
   CKX(cudaMemcpyAsync(flags, ctx->d_flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
   CKX(cudaStreamSynchronize(ctx->stream));
   cudaFree(d_pt);
   cudaFree(d_wt);
   if (flags[FLAG_CGFAIL]) {
-    ctx->err = "L2 projection of init_rho did not converge";
+    ctx->err = std::string("L2 projection of ") + what + " did not converge";
     return MSGPU_ERR_NO_CONVERGENCE;
   }
+  return MSGPU_OK;
+}
+
+int build_tables_at(msgpu_ctx* ctx, double t);
+
+// MicroSolver::set_exact_solution (micro.cpp:224-234, bio micro.cpp:381-391, rho_solver.cpp:353-359)
+int set_exact_solution(msgpu_ctx* ctx, double t) {
+  if (ctx->pp.prog_err < 0) {
+    ctx->err = "no exact solution was set (msgpu_set_function(MSGPU_FN_SOLUTION, ...))";
+    return MSGPU_ERR_INVALID;
+  }
+  int qe = ctx->desc.q_degree;  // QGauss(fem_q_deg) in the elliptic and bio drivers
+  if (ctx->desc.problem == MSGPU_PARABOLIC) {
+    qe = 3;  // rho_solver.cpp:357
+    const int rc = build_tables_at(ctx, t);
+    if (rc) return rc;
+  }
+  return project_into_solutions(ctx, ctx->pp.ps.point_program(ctx->pp.prog_err), qe, "the exact solution");
+}
+
+// ------------------------------------------------------------------------------------------------
+// parabolic: shared stencils built on the host (n entries, closed-form Q1 local matrices on a
+// square cell: what MatrixCreator::create_mass_matrix / create_laplace_matrix with QGauss(2)
+// integrate exactly, rho_solver.cpp:64-65)
+int parabolic_setup(msgpu_ctx* ctx) {
+  CKX(cudaSetDevice(ctx->device));
+  const MeshDims& md = ctx->md;
+  const int N = ctx->N;
+  int rc;
+  if ((rc = ensure(ctx, &ctx->d_mass, static_cast<size_t>(NDIAG) * md.ld))) return rc;
+  if ((rc = ensure(ctx, &ctx->d_lumped, static_cast<size_t>(md.n)))) return rc;
+  std::vector<double> mass, sys, lumped;
+  build_stencils(md, 0.0, ctx->scalars[3], ctx->scalars[0], ctx->scalars[2], mass, sys, lumped);
+  CKX(cudaMemcpy(ctx->d_mass, mass.data(), sizeof(double) * mass.size(), cudaMemcpyHostToDevice));
+  CKX(cudaMemcpy(ctx->d_lumped, lumped.data(), sizeof(double) * lumped.size(), cudaMemcpyHostToDevice));
+  ctx->parabolic_dt = -1.0;
+  if (ctx->pp.prog_init < 0) return MSGPU_OK;  // start from zero
+  // rho_k^0 = L2 projection of init_rho(x_k, .) with QGauss(3) (rho_solver.cpp:78-83)
+  if ((rc = project_into_solutions(ctx, ctx->pp.ps.point_program(ctx->pp.prog_init), 3, "init_rho"))) return rc;
+  CKX(cudaMemcpyAsync(ctx->d_xold, ctx->d_x, sizeof(double) * N * md.n, cudaMemcpyDeviceToDevice, ctx->stream));
+  CKX(cudaStreamSynchronize(ctx->stream));
   return MSGPU_OK;
 }
 

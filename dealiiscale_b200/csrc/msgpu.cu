@@ -139,6 +139,7 @@ int parabolic_setup(msgpu_ctx* ctx);                       // kernels_extra.cu /
 int parabolic_assemble(msgpu_ctx* ctx, double dt, double t);
 int compute_errors(msgpu_ctx* ctx, double* l2, double* h1);
 int compute_residuals(msgpu_ctx* ctx, double* l2);
+int set_exact_solution(msgpu_ctx* ctx, double t);
 int comm_allgather_coupling(msgpu_ctx* ctx, double* c0, double* c1);
 int comm_block(const msgpu_ctx* ctx);
 void comm_destroy(msgpu_ctx* ctx);
@@ -635,6 +636,10 @@ int msgpu_errors(msgpu_ctx* ctx, double* l2, double* h1) {
 int msgpu_residuals(msgpu_ctx* ctx, double* l2) {
   if (!ctx || !ctx->setup_done || !l2) return MSGPU_ERR_INVALID;
   return compute_residuals(ctx, l2);
+}
+int msgpu_set_exact_solution(msgpu_ctx* ctx, double t) {
+  if (!ctx || !ctx->setup_done) return MSGPU_ERR_INVALID;
+  return set_exact_solution(ctx, t);
 }
 
 static int copy_vectors_out(msgpu_ctx* ctx, const double* dev, int k0, int k1, double* out) {

@@ -7,6 +7,7 @@
 #include <fstream>
 
 #include "micro_solver.h"
+#include "output.h"
 
 namespace ms {
 namespace bio {
@@ -242,10 +243,53 @@ class Manager {
                       std::to_string(macro_solver.mesh.n), sci3(r.mL2), sci3(r.mH1), sci3(r.ML2), sci3(r.MH1)});
     return format_table({"cycle", "cells", "dofs", "mL2", "mH1", "ML2", "MH1"}, rows);
   }
-  void output_results() {  // manager.cpp:111-123 (VTK output of :125-178 is not reproduced)
-    if (!functions.data.params.get_bool("has_solution") || ct_file_name.empty()) return;
-    std::ofstream out(ct_file_name, std::ios::app);
-    out << convergence_table();
+  void output_results() {  // manager.cpp:111-123
+    if (ct_file_name.empty()) return;
+    if (functions.data.params.get_bool("has_solution")) {
+      std::ofstream out(ct_file_name, std::ios::app);
+      out << convergence_table();
+    }
+    if (solution_files_enabled()) patch_and_write_solutions();
+  }
+  // manager.cpp:125-178: one VTK file per micro grid, as the reference writes them
+  void patch_and_write_solutions() {
+    ensure_directory(output_dir + "/micro-solutions");
+    write_vtk_file(output_dir + "/u-solution.vtk", macro_solver.mesh, macro_solver.sol_u, "u");
+    write_vtk_file(output_dir + "/w-solution.vtk", macro_solver.mesh, macro_solver.sol_w, "w");
+    write_micro_grid_locations(output_dir + "/micro-solutions/grid_locations.txt");
+    MacroMesh micro_mesh;
+    micro_mesh.build(MSGPU_MESH_SUBDIVIDED, micro_solver.cells_per_axis());
+    const unsigned int num_grids = micro_solver.get_num_grids();
+    const int n = micro_solver.n_dofs();
+    const int some_int = static_cast<int>(num_grids / 2);
+    std::vector<double> computed_mid;
+    const unsigned int batch = 256;  // grids fetched from the device per copy
+    std::vector<double> buf, one(n);
+    for (unsigned int k0 = 0; k0 < num_grids; k0 += batch) {
+      const unsigned int k1 = std::min(num_grids, k0 + batch);
+      micro_solver.solutions_range(k0, k1, buf);
+      for (unsigned int k = k0; k < k1; ++k) {
+        std::copy(buf.begin() + static_cast<size_t>(k - k0) * n, buf.begin() + static_cast<size_t>(k - k0 + 1) * n,
+                  one.begin());
+        if (static_cast<int>(k) == some_int) computed_mid = one;
+        write_vtk_file(output_dir + "/micro-solutions/v-solution-" + std::to_string(k) + ".vtk", micro_mesh, one, "v");
+      }
+    }
+    if (functions.data.params.get_bool("has_solution")) {
+      std::printf("Exact micro-solution set\n");
+      micro_solver.set_exact_solution();
+      const std::vector<double> exact = micro_solver.solution(some_int);
+      std::vector<double> error(computed_mid);
+      for (size_t i = 0; i < error.size(); ++i) error[i] -= exact[i];
+      write_vtk_file(output_dir + "/micro-error.vtk", micro_mesh, error, "v");
+      write_vtk_file(output_dir + "/micro-exact.vtk", micro_mesh, exact, "v");
+    }
+  }
+  void write_micro_grid_locations(const std::string& filename) {  // manager.cpp:181-195
+    std::printf("Writing grid locations to file\n");
+    std::vector<std::array<double, 2>> grid_locations;
+    macro_solver.get_dof_locations(grid_locations);
+    write_grid_locations(filename, grid_locations, micro_solver.get_num_grids());
   }
 
   Functions functions;
@@ -256,6 +300,7 @@ class Manager {
   double error_eps = 1e-2, residual_eps = 1e-5, max_iterations = 1e4;
   int cycle_limit = -1;
   bool keep_solutions = false;
+  std::string output_dir = "results";
   std::vector<CycleRecord> history;
 
  private:

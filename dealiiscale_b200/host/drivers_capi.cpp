@@ -30,6 +30,40 @@ extern "C" {
 
 const char* msdrv_last_error() { return g_error.c_str(); }
 
+// ---- solution files (output.h): host-only, no device involved -----------------------------------
+// format 0 = DataOut::write_gnuplot, 1 = DataOut::write_vtk; nodal[(nc+1)^2] in the reference numbering of the mesh kind
+int msdrv_write_solution(const char* path, int format, int mesh_kind, int cells_per_axis, const double* nodal,
+                         const char* name) {
+  return guarded([&] {
+    ms::MacroMesh mesh;
+    mesh.build(mesh_kind, cells_per_axis);
+    const std::vector<double> v(nodal, nodal + mesh.n);
+    if (format == 0) ms::write_gnuplot_file(path, mesh, v, name);
+    else ms::write_vtk_file(path, mesh, v, name);
+    return 0;
+  });
+}
+int msdrv_write_grid_locations(const char* path, const double* xy, int n) {
+  return guarded([&] {
+    std::vector<std::array<double, 2>> loc(n);
+    for (int i = 0; i < n; ++i) loc[i] = {xy[2 * i], xy[2 * i + 1]};
+    ms::write_grid_locations(path, loc, n);
+    return 0;
+  });
+}
+// support points of the mesh in its reference numbering, xy[(nc+1)^2][2]
+int msdrv_mesh_points(int mesh_kind, int cells_per_axis, double* xy) {
+  return guarded([&] {
+    ms::MacroMesh mesh;
+    mesh.build(mesh_kind, cells_per_axis);
+    for (int d = 0; d < mesh.n; ++d) {
+      xy[2 * d] = mesh.x_of(d);
+      xy[2 * d + 1] = mesh.y_of(d);
+    }
+    return 0;
+  });
+}
+
 // ---- solve_elliptic -----------------------------------------------------------------------------
 void* msdrv_elliptic_create(const char* prm, int macro_ref, int micro_ref) {
   try {

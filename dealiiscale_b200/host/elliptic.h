@@ -5,6 +5,7 @@
 #include <fstream>
 
 #include "micro_solver.h"
+#include "output.h"
 
 namespace ms {
 namespace elliptic {
@@ -172,10 +173,31 @@ class Manager {
                       std::to_string(macro_solver.mesh.n), sci3(r.mL2), sci3(r.mH1), sci3(r.ML2), sci3(r.MH1)});
     return format_table({"cycle", "cells", "dofs", "mL2", "mH1", "ML2", "MH1"}, rows);
   }
-  void output_results() {  // manager.cpp:79-88 (the gnuplot dumps of :91-131 are not reproduced)
+  void output_results() {  // manager.cpp:79-88
     if (ct_file_name.empty()) return;
-    std::ofstream out(ct_file_name, std::ios::app);
-    out << convergence_table();
+    {
+      std::ofstream out(ct_file_name, std::ios::app);
+      out << convergence_table();
+    }
+    if (solution_files_enabled()) patch_and_write_solutions();
+  }
+  // manager.cpp:91-131.  NB micro-error.gpl holds (computed - projected exact) of the middle grid and, like the
+  // reference, this leaves the PROJECTED EXACT solutions in the micro solver.
+  void patch_and_write_solutions() {
+    ensure_directory(output_dir);
+    write_gnuplot_file(output_dir + "/macro-solution.gpl", macro_solver.mesh, macro_solver.solution, "solution");
+    MacroMesh micro_mesh;
+    micro_mesh.build(MSGPU_MESH_REFINE_GLOBAL, micro_solver.cells_per_axis());
+    const int some_int = static_cast<int>(micro_solver.get_num_grids() / 2);
+    const std::vector<double> computed = micro_solver.solution(some_int);
+    write_gnuplot_file(output_dir + "/micro-computed.gpl", micro_mesh, computed, "solution");
+    std::printf("Exact micro-solution set\n");
+    micro_solver.set_exact_solution();
+    const std::vector<double> exact = micro_solver.solution(some_int);
+    std::vector<double> error(computed);
+    for (size_t i = 0; i < error.size(); ++i) error[i] -= exact[i];
+    write_gnuplot_file(output_dir + "/micro-error.gpl", micro_mesh, error, "solution");
+    write_gnuplot_file(output_dir + "/micro-exact.gpl", micro_mesh, exact, "solution");
   }
 
   Functions functions;
@@ -184,6 +206,7 @@ class Manager {
   double eps = 1e-4, max_iterations = 1e4;
   int cycle_limit = -1;      // extension for K-cycle parity runs on the diverging parameter sets
   bool keep_solutions = false;
+  std::string output_dir = "results";  // the reference writes into results/ of the working directory
   std::vector<CycleRecord> history;
 
  private:

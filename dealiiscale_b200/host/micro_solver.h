@@ -56,6 +56,7 @@ class MicroSolver {
   }
   unsigned int get_num_grids() const { return num_grids_; }
   int n_dofs() const { return n_dofs_; }
+  int cells_per_axis() const { return cells_; }
 
   void assemble_system() {
     push_macro();
@@ -104,11 +105,17 @@ class MicroSolver {
     grid_residuals(r);
     l2_residual = nodal_l2_norm(macro_mesh, r, q);
   }
+  // micro.cpp:224-234, bio micro.cpp:381-391, rho_solver.cpp:353-359 (t: parabolic only)
+  void set_exact_solution(double t = 0.0) { check(msgpu_set_exact_solution(ctx_, t)); }
   // `solutions` of the reference (micro.h:97), reference DoF numbering
   std::vector<double> solution(int k) {
     std::vector<double> out(n_dofs_);
     check(msgpu_get_solutions(ctx_, k, k + 1, out.data()));
     return out;
+  }
+  void solutions_range(int k0, int k1, std::vector<double>& out) {
+    out.assign(static_cast<size_t>(k1 - k0) * n_dofs_, 0.0);
+    check(msgpu_get_solutions(ctx_, k0, k1, out.data()));
   }
   void all_solutions(std::vector<double>& out) {
     out.assign(static_cast<size_t>(num_grids_) * n_dofs_, 0.0);

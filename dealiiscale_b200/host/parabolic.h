@@ -1,10 +1,12 @@
 // solve_parabolic: elliptic-parabolic two-scale driver on top of the GPU micro path.
 // Host mirror of reference src/elliptic-parabolic/{pi_solver,time_manager}.{h,cpp} and two_scale.cpp.
 #pragma once
+#include <cmath>
 #include <cstdio>
 #include <fstream>
 
 #include "micro_solver.h"
+#include "output.h"
 
 namespace ms {
 namespace parabolic {
@@ -205,6 +207,7 @@ class TimeManager {
       functions.set_time(time);  // iterate(): time_manager.cpp:65-70
       pi_solver.iterate();
       rho_solver.iterate(time_step, time);
+      write_plot();
       StepRecord r;
       r.it = it;
       r.time = time;
@@ -231,10 +234,54 @@ class TimeManager {
     }
     return format_table({"iteration", "time", "cells", "dofs", "mL2", "ML2", "mH1", "MH1"}, rows);
   }
-  void output_results() {  // time_manager.cpp:111-119 (plot files are not reproduced)
+  // time_manager.cpp:92-109, called after every time step (:69)
+  void write_plot() {
+    if (ct_file_name.empty() || !solution_files_enabled()) return;
+    ensure_directory(output_dir);
+    write_vtk_file(output_dir + "/micro-solution" + int_to_string(it, 3) + ".vtk", micro_mesh(), rho_solver.solution(0),
+                   "solution");
+    write_vtk_file(output_dir + "/macro-solution" + int_to_string(it, 3) + ".vtk", pi_solver.mesh, pi_solver.solution,
+                   "solution");
+  }
+  void output_results() {  // time_manager.cpp:111-143
     if (ct_file_name.empty()) return;
-    std::ofstream out(ct_file_name, std::ios::app);
-    out << convergence_table();
+    {
+      std::ofstream out(ct_file_name, std::ios::app);
+      out << convergence_table();
+    }
+    if (!solution_files_enabled()) return;
+    ensure_directory(output_dir);
+    write_gnuplot_file(output_dir + "/final_macro_solution.gpl", pi_solver.mesh, pi_solver.solution, "solution");
+    const unsigned int index = rho_solver.get_num_grids() / 2;
+    write_gnuplot_file(output_dir + "/final_micro_solution.gpl", micro_mesh(), rho_solver.solution(index), "solution");
+    std::vector<std::array<double, 2>> dof_locations;
+    pi_solver.get_dof_locations(dof_locations);
+    patch_micro_solutions(dof_locations);
+  }
+  // RhoSolver::patch_micro_solutions (rho_solver.cpp:240-283): every micro solution drawn on a small copy of the
+  // micro mesh centred at its macro point, all into one gnuplot file
+  void patch_micro_solutions(const std::vector<std::array<double, 2>>& locations) {
+    std::ofstream output(output_dir + "/patched_micro_solution.gpl");
+    const double side_length = std::pow(static_cast<double>(locations.size()), 0.5);
+    const double size = 1.0 / (static_cast<int>(side_length) - 1);  // get_micro_grid_size
+    const double micro_size = 2 * size;
+    const MacroMesh& mm = micro_mesh();
+    std::vector<double> all;
+    rho_solver.all_solutions(all);
+    const size_t n = rho_solver.n_dofs();
+    std::vector<double> one(n);
+    for (size_t i = 0; i < locations.size(); ++i) {
+      std::copy(all.begin() + i * n, all.begin() + (i + 1) * n, one.begin());
+      Placement pl;
+      pl.x0 = -0.5 * micro_size + locations[i][0];
+      pl.y0 = -0.5 * micro_size + locations[i][1];
+      pl.width = micro_size;
+      write_gnuplot(output, mm, one, "solution", pl);
+    }
+  }
+  const MacroMesh& micro_mesh() {
+    if (micro_mesh_.n == 0) micro_mesh_.build(MSGPU_MESH_SUBDIVIDED, rho_solver.cells_per_axis());
+    return micro_mesh_;
   }
 
   Functions functions;
@@ -243,11 +290,13 @@ class TimeManager {
   double time_step, final_time = 0.5, time = 0;
   int step_limit = -1;
   bool keep_solutions = false;
+  std::string output_dir = "results";
   std::vector<StepRecord> history;
 
  private:
   int it = 0;
   std::string ct_file_name;
+  MacroMesh micro_mesh_;
 };
 
 }  // namespace parabolic

@@ -12,6 +12,7 @@ reference (C++)                        here
 ``set_macro_solution(&sol, &dofh)``    ``set_macro_solution(u, w=None)``     micro.cpp:97-100
 ``run()`` / ``assemble_and_solve_all``  ``run()``                             micro.cpp:218-221
 ``solutions``                          ``solutions()``                       micro.h:97
+``set_exact_solution()``               ``set_exact_solution(t=0)``           micro.cpp:224-234
 ``RhoSolver::iterate(dt)``             ``iterate(dt, t)``                    rho_solver.cpp:232-237
 ``MacroSolver::compute_microscopic_contribution``  ``coupling()``           macro.cpp:162-166
 =====================================  =======================================================
@@ -198,6 +199,11 @@ class MicroSolver:
         l2 = np.zeros(self.num_grids)
         self._check(self.lib.msgpu_residuals(self.h, _d(l2)))
         return l2
+
+    def set_exact_solution(self, t=0.0):
+        """solutions[k] = L2 projection of the exact micro solution at x_k (micro.cpp:224-234, bio micro.cpp:381-391,
+        rho_solver.cpp:353-359; ``t`` only matters for the parabolic problem)."""
+        self._check(self.lib.msgpu_set_exact_solution(self.h, float(t)))
 
     def solutions(self, k0=0, k1=None):
         k1 = self.num_grids if k1 is None else k1

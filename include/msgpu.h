@@ -140,6 +140,14 @@ int msgpu_coupling(msgpu_ctx* ctx, double* c0, double* c1);
 int msgpu_errors(msgpu_ctx* ctx, double* l2, double* h1);
 int msgpu_residuals(msgpu_ctx* ctx, double* l2);
 
+/* ---- MicroSolver::set_exact_solution (micro.cpp:224-234; bio micro.cpp:381-391; RhoSolver
+ * rho_solver.cpp:353-359): solutions[k] = VectorTools::project(QGauss(q_degree | 3 parabolic),
+ * exact solution at x_k) for every grid — a batched L2 projection (load vectors + CG on the shared
+ * mass stencil).  t: time of the exact solution (parabolic only).  Overwrites the solutions and the
+ * right-hand sides; the reference uses it for the micro-exact / micro-error output files
+ * (manager.cpp:107-128, bio manager.cpp:156-181). */
+int msgpu_set_exact_solution(msgpu_ctx* ctx, double t);
+
 /* ---- public data of MicroSolver: solutions (micro.h:97), in reference DoF numbering -------- */
 int msgpu_get_solutions(msgpu_ctx* ctx, int k0, int k1, double* out /* [k1-k0][n] */);
 int msgpu_set_solutions(msgpu_ctx* ctx, int k0, int k1, const double* in);

@@ -274,6 +274,13 @@ struct MicroSolver {
     for (auto& e : errors)
       if (!e.empty()) throw std::runtime_error(e);
   }
+  // micro.cpp:381-391: every solution vector becomes the L2 projection of solution_v (QGauss(fem_q_deg))
+  void set_exact_solution() {
+    for (int k = 0; k < num_grids; ++k) {
+      const double* x = grid_locations[k].data();
+      solutions[k] = l2_project(grid, pattern, fem_q_deg, [&](const double* y) { return data.solution_v.mvalue(x, y); });
+    }
+  }
   // micro.cpp:317-338 per grid
   void grid_errors(int k, double& l2, double& h1) const {
     const int p = fem_q_deg;

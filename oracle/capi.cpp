@@ -167,6 +167,12 @@ void orc_ell_bulk(void* h, double* c) {
   auto* m = static_cast<elliptic::Manager*>(h);
   for (int k = 0; k < m->micro_solver.num_grids; ++k) c[k] = m->macro_solver.get_micro_bulk(k);
 }
+int orc_ell_set_exact_solution(void* h) {
+  return guarded([&] {
+    static_cast<elliptic::Manager*>(h)->micro_solver.set_exact_solution();
+    return 0;
+  });
+}
 void orc_ell_grid_errors(void* h, double* l2, double* h1) {
   auto* m = static_cast<elliptic::Manager*>(h);
   for (int k = 0; k < m->micro_solver.num_grids; ++k) m->micro_solver.grid_errors(k, l2[k], h1[k]);

@@ -327,6 +327,13 @@ struct MicroSolver {
     if (!r.converged) throw std::runtime_error("micro CG: SolverControl::NoConvergence");
     cg_iterations[k] = r.iterations;
   }
+  // micro.cpp:224-234: every solution vector becomes the L2 projection of the exact micro solution
+  void set_exact_solution() {
+    for (int k = 0; k < num_grids; ++k) {
+      const double* x = grid_locations[k].data();
+      solutions[k] = l2_project(grid, pattern, fem_q_deg, [&](const double* y) { return data.micro_solution.mvalue(x, y); });
+    }
+  }
   void run() {  // micro.cpp:218-221
     assemble_system();
     solve();

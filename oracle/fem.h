@@ -314,6 +314,41 @@ inline CGResult solve_cg(const SparseMatrix& A, std::vector<double>& x, const st
   }
 }
 
+// VectorTools::project(mapping, dof_handler, constraints, QGauss<2>(p), f, vec) for Q1 on the square mesh:
+// mass matrix and load vector with the given rule (the Q1 mass matrix is integrated exactly for p >= 2),
+// CG to 1e-12 relative to the load (deal.II 9.1: ReductionControl(5 n, 0., 1e-12)).  Called by the
+// reference at src/elliptic-elliptic/micro.cpp:231, src/bio-multiscale/micro.cpp:388,
+// src/elliptic-parabolic/rho_solver.cpp:357.  f(y) = value at the micro point y.
+template <class F>
+inline std::vector<double> l2_project(const Grid& grid, const SparsityPattern& pattern, int p, F&& f) {
+  std::vector<double> qx, qw;
+  gauss01(p, qx, qw);
+  const double h = grid.h;
+  const int n = grid.n_dofs();
+  SparseMatrix mass;
+  mass.reinit(pattern);
+  std::vector<double> rhs(n, 0.0), sol(n, 0.0);
+  for (int c = 0; c < grid.n_cells(); ++c) {
+    const auto& cd = grid.cell_dofs[c];
+    for (int qj = 0; qj < p; ++qj)
+      for (int qi = 0; qi < p; ++qi) {
+        double v[4];
+        q1_values(qx[qi], qx[qj], v);
+        const double y[2] = {grid.cell_x0(c) + h * qx[qi], grid.cell_y0(c) + h * qx[qj]};
+        const double JxW = qw[qi] * qw[qj] * h * h;
+        const double fv = f(y);
+        for (int i = 0; i < 4; ++i) {
+          rhs[cd[i]] += fv * v[i] * JxW;
+          for (int j = 0; j < 4; ++j) mass.add(cd[i], cd[j], v[i] * v[j] * JxW);
+        }
+      }
+  }
+  double nrm = 0;
+  for (double r : rhs) nrm += r * r;
+  solve_cg(mass, sol, rhs, 10 * n + 100, 1e-12 * std::sqrt(nrm));
+  return sol;
+}
+
 // Evaluate a nodal Q1 field at unit-cell point (xi,eta) of cell c.
 inline double q1_interp(const Grid& g, const std::vector<double>& u, int c, double xi, double eta) {
   double v[4];

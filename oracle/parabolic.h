@@ -262,6 +262,10 @@ struct RhoSolver {
     solve_time_step();
     old_solutions = solutions;
   }
+  // rho_solver.cpp:353-359: every solution vector becomes the L2 projection of the exact rho at the current time
+  void set_exact_solution() {
+    for (int k = 0; k < num_grids; ++k) solutions[k] = project(data.micro_solution, grid_locations[k].data());
+  }
   // per-grid part of compute_error (:307-330): L2 and "H1" (integrate_difference with H1_norm,
   // accumulated as an l2 norm over cells) against micro_solution(x_k, ., t), QGauss(3)
   void grid_errors(int k, double& l2, double& h1) const {

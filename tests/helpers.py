@@ -287,6 +287,10 @@ class OracleElliptic:
         self.lib.orc_ell_grid_errors(self.h, dptr(l2), dptr(h1))
         return l2, h1
 
+    def set_exact_solution(self):
+        if self.lib.orc_ell_set_exact_solution(self.h) != 0:
+            raise RuntimeError(self.lib.orc_last_error().decode())
+
     def run(self, cycle_limit=-1):
         r = self.lib.orc_ell_run(self.h, cycle_limit)
         if r < 0:
@@ -396,6 +400,10 @@ class OracleBio:
         l2, h1 = np.zeros(self.N), np.zeros(self.N)
         self.lib.orc_bio_grid_errors(self.h, dptr(l2), dptr(h1))
         return l2, h1
+
+    def set_exact_solution(self):
+        if self.lib.orc_bio_set_exact_solution(self.h) != 0:
+            raise RuntimeError(self.lib.orc_last_error().decode())
 
     def grid_residuals(self):
         l2 = np.zeros(self.N)
@@ -510,6 +518,10 @@ class OracleParabolic:
         l2, h1 = np.zeros(self.N), np.zeros(self.N)
         self.lib.orc_par_grid_errors(self.h, dptr(l2), dptr(h1))
         return l2, h1
+
+    def set_exact_solution(self, t):
+        if self.lib.orc_par_set_exact_solution(self.h, C.c_double(t)) != 0:
+            raise RuntimeError(self.lib.orc_last_error().decode())
 
     def run(self, step_limit=-1):
         r = self.lib.orc_par_run(self.h, step_limit)

@@ -135,6 +135,43 @@ def test_cli_binaries_run_and_write_the_table(tmp_path):
     assert "Results: 'macro_refinement', 'micro_refinement', 'num_threads', 'wall_time', 'cpu_time'" in r.stdout
     table = open(os.path.join(tmp_path, "results", "out.txt")).read()
     assert table.split()[:7] == ["cycle", "cells", "dofs", "mL2", "mH1", "ML2", "MH1"]
+    # the solution files of bio manager.cpp:125-195 (2x2 macro cells -> 9 micro grids of 3x3 cells)
+    res = os.path.join(tmp_path, "results")
+    for f in ["u-solution.vtk", "w-solution.vtk", "micro-error.vtk", "micro-exact.vtk", "micro-solutions/grid_locations.txt"] \
+            + [f"micro-solutions/v-solution-{k}.vtk" for k in range(9)]:
+        assert os.path.getsize(os.path.join(res, f)) > 0, f
+    assert len(open(os.path.join(res, "micro-solutions", "grid_locations.txt")).read().split()) == 18
+    from test_output_files import parse_vtk
+
+    pts, cells, types, name, data = parse_vtk(os.path.join(res, "micro-exact.vtk"))
+    assert name == "v" and len(cells) == 9 and np.isfinite(data).all()
+    # linear.prm has a manufactured solution: the projected exact solution minus the computed one is small
+    _, _, _, _, err = parse_vtk(os.path.join(res, "micro-error.vtk"))
+    assert np.abs(err).max() < 0.5 * np.abs(data).max()
+
+
+def test_elliptic_and_parabolic_binaries_write_their_solution_files(tmp_path):
+    os.makedirs(os.path.join(tmp_path, "results"), exist_ok=True)
+    os.symlink(INPUT, os.path.join(tmp_path, "input"))
+    exe = os.path.join(ROOT, "dealiiscale_b200", "_build", "solve_parabolic")
+    r = subprocess.run([exe, "input/linear_time.prm", "1"], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr
+    res = os.path.join(tmp_path, "results")
+    for f in ("final_macro_solution.gpl", "final_micro_solution.gpl", "patched_micro_solution.gpl",
+              "micro-solution001.vtk", "macro-solution002.vtk", "linear_time_convergence_table.txt"):
+        assert os.path.getsize(os.path.join(res, f)) > 0, f
+    # 81 micro grids of 8x8 cells, each with its own gnuplot header (rho_solver.cpp:249-265)
+    patched = open(os.path.join(res, "patched_micro_solution.gpl")).read()
+    assert patched.count("# <x> <y> <solution> ") == 81
+    exe = os.path.join(ROOT, "dealiiscale_b200", "_build", "solve_elliptic")
+    r = subprocess.run([exe, "input/elliptic_linear.prm"], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr
+    for f in ("macro-solution.gpl", "micro-computed.gpl", "micro-error.gpl", "micro-exact.gpl",
+              "elliptic_linear_convergence_table.txt"):
+        assert os.path.getsize(os.path.join(res, f)) > 0, f
+    rows = [ln.split() for ln in open(os.path.join(res, "micro-error.gpl")) if ln.strip() and ln[0] != "#"]
+    err = np.array(rows, dtype=float)[:, 2]
+    assert len(err) == 4 * 32 * 32 and np.abs(err).max() < 1e-2  # finest level: computed - projected exact
 
 
 def test_device_and_host_macro_paths_agree():
