@@ -365,6 +365,14 @@ def main():
 
     step_bytes, cg_bytes = algorithmic_bytes(n, nnz, its, n_total)
     if rank == 0:
+        # FLOPs of one CG step: SpMV 2 nnz, two dot products 4 n, three vector updates 6 n (this rank's systems)
+        cg_flops = float(its.sum()) * (2.0 * nnz + 10.0 * n)
+        sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+        n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        fp64_peak = n_sms * 64 * 2 * sm_mhz * 1e6 / 1e12  # 64 DFMA lanes per SM and clock (ncu: sm__inst_executed_pipe_fp64)
+        fp64 = {"achieved": cg_flops / (cg_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": cg_flops / (cg_ms * 1e-3) / 1e12 / fp64_peak,
+                "peak_source": f"{n_sms} SMs x 64 FP64 FMA/clk x {sm_mhz:.0f} MHz (nominal)"}
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak = json.load(open(peaks_path))["hbm_gbs"]
@@ -399,6 +407,8 @@ def main():
                 "step_algorithmic_bytes": step_bytes,
                 "step_achieved_GBps": step_bytes / (dev_ms_step * 1e-3) / 1e9,
                 "frac_of_nominal_8TBps": achieved / 8000.0,
+                # what actually bounds the on-chip solver: FP64 issue + the latency of two block-wide reductions per step
+                "fp64": fp64,
             },
             "phases_ms_per_step": {k: st[k] / args.steps for k in
                                    ("ms_tables", "ms_moments", "ms_gather", "ms_cg", "ms_coupling")},
