@@ -281,6 +281,47 @@ int msgpu_comm_p2p_attach(msgpu_ctx* ctx, const unsigned char* handles) {
   return MSGPU_OK;
 }
 
+// Per-grid scalars of all ranks (error / residual norms for the stop test):
+// local[fields][N of this rank] -> all[fields][n_total] on every rank.  Host buffers, staged through the
+// padded gather scratch; one grouped ncclAllGather.  Without a communicator it is a copy.
+int msgpu_comm_allgather(msgpu_ctx* ctx, const double* local, double* all, int fields) {
+  if (!ctx || !local || !all || fields < 1 || fields > 2) return MSGPU_ERR_INVALID;
+  if (!ctx->comm_ready || ctx->n_ranks == 1) {
+    std::memcpy(all, local, sizeof(double) * static_cast<size_t>(fields) * ctx->N);
+    return MSGPU_OK;
+  }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return MSGPU_ERR_CUDA;
+  ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm);
+  if (!comm) {
+    ctx->err = "msgpu_comm_allgather needs the NCCL communicator (msgpu_comm_init with an id)";
+    return MSGPU_ERR_COMM;
+  }
+  const int B = comm_block(ctx);
+  const size_t padded = static_cast<size_t>(B) * ctx->n_ranks;
+  const NcclApi& nc = nccl_api();
+  for (int f = 0; f < fields; ++f)
+    cudaMemcpyAsync(ctx->d_macro + f * padded + static_cast<size_t>(ctx->rank) * B, local + static_cast<size_t>(f) * ctx->N,
+                    sizeof(double) * ctx->N, cudaMemcpyHostToDevice, ctx->stream);
+  ncclResult_t r = nc.GroupStart();
+  if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclGroupStart");
+  for (int f = 0; f < fields; ++f) {
+    double* base = ctx->d_macro + f * padded;
+    r = nc.AllGather(base + static_cast<size_t>(ctx->rank) * B, base, B, ncclDouble, comm, ctx->stream);
+    if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclAllGather");
+  }
+  r = nc.GroupEnd();
+  if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclGroupEnd");
+  ctx->launches += 1;
+  for (int f = 0; f < fields; ++f)
+    cudaMemcpyAsync(all + static_cast<size_t>(f) * ctx->n_total, ctx->d_macro + f * padded, sizeof(double) * ctx->n_total,
+                    cudaMemcpyDeviceToHost, ctx->stream);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    ctx->err = "allgather failed";
+    return MSGPU_ERR_CUDA;
+  }
+  return MSGPU_OK;
+}
+
 // u_all / w_all: [n_total] host arrays; significant on root, overwritten on the other ranks.
 int msgpu_broadcast_macro(msgpu_ctx* ctx, double* u_all, double* w_all, int root) {
   if (!ctx || !ctx->comm_ready || !ctx->setup_done || !u_all) return MSGPU_ERR_INVALID;

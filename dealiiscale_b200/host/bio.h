@@ -243,30 +243,33 @@ class Manager {
                       std::to_string(macro_solver.mesh.n), sci3(r.mL2), sci3(r.mH1), sci3(r.ML2), sci3(r.MH1)});
     return format_table({"cycle", "cells", "dofs", "mL2", "mH1", "ML2", "MH1"}, rows);
   }
-  void output_results() {  // manager.cpp:111-123
+  void output_results() {  // manager.cpp:111-123; several ranks: rank 0 writes the table and the macro files
     if (ct_file_name.empty()) return;
-    if (functions.data.params.get_bool("has_solution")) {
+    if (functions.data.params.get_bool("has_solution") && distributed().rank == 0) {
       std::ofstream out(ct_file_name, std::ios::app);
       out << convergence_table();
     }
     if (solution_files_enabled()) patch_and_write_solutions();
   }
-  // manager.cpp:125-178: one VTK file per micro grid, as the reference writes them
+  // manager.cpp:125-178: one VTK file per micro grid, as the reference writes them; every rank writes the
+  // grids it owns (numbered globally), the owner of the middle grid writes micro-error / micro-exact
   void patch_and_write_solutions() {
     ensure_directory(output_dir + "/micro-solutions");
-    write_vtk_file(output_dir + "/u-solution.vtk", macro_solver.mesh, macro_solver.sol_u, "u");
-    write_vtk_file(output_dir + "/w-solution.vtk", macro_solver.mesh, macro_solver.sol_w, "w");
-    write_micro_grid_locations(output_dir + "/micro-solutions/grid_locations.txt");
+    if (distributed().rank == 0) {
+      write_vtk_file(output_dir + "/u-solution.vtk", macro_solver.mesh, macro_solver.sol_u, "u");
+      write_vtk_file(output_dir + "/w-solution.vtk", macro_solver.mesh, macro_solver.sol_w, "w");
+      write_micro_grid_locations(output_dir + "/micro-solutions/grid_locations.txt");
+    }
     MacroMesh micro_mesh;
     micro_mesh.build(MSGPU_MESH_SUBDIVIDED, micro_solver.cells_per_axis());
-    const unsigned int num_grids = micro_solver.get_num_grids();
+    const unsigned int first = micro_solver.first_grid(), last = first + micro_solver.get_num_local_grids();
     const int n = micro_solver.n_dofs();
-    const int some_int = static_cast<int>(num_grids / 2);
+    const int some_int = static_cast<int>(micro_solver.get_num_grids() / 2);
     std::vector<double> computed_mid;
     const unsigned int batch = 256;  // grids fetched from the device per copy
     std::vector<double> buf, one(n);
-    for (unsigned int k0 = 0; k0 < num_grids; k0 += batch) {
-      const unsigned int k1 = std::min(num_grids, k0 + batch);
+    for (unsigned int k0 = first; k0 < last; k0 += batch) {
+      const unsigned int k1 = std::min(last, k0 + batch);
       micro_solver.solutions_range(k0, k1, buf);
       for (unsigned int k = k0; k < k1; ++k) {
         std::copy(buf.begin() + static_cast<size_t>(k - k0) * n, buf.begin() + static_cast<size_t>(k - k0 + 1) * n,
@@ -275,7 +278,7 @@ class Manager {
         write_vtk_file(output_dir + "/micro-solutions/v-solution-" + std::to_string(k) + ".vtk", micro_mesh, one, "v");
       }
     }
-    if (functions.data.params.get_bool("has_solution")) {
+    if (functions.data.params.get_bool("has_solution") && micro_solver.owns(some_int)) {
       std::printf("Exact micro-solution set\n");
       micro_solver.set_exact_solution();
       const std::vector<double> exact = micro_solver.solution(some_int);

@@ -1,0 +1,127 @@
+// One process per GPU for the C++ drivers: which rank this process is and a small
+// out-of-band exchange for the two things the ranks must agree on before the first kernel — the 128-byte
+// NCCL unique id and the 64-byte peer-memory handles of msgpu_comm_p2p_export.
+//
+// No reference call site: the reference is a single process (manager.cpp:25-26 hands raw pointers from the
+// micro to the macro solver).  Launch as `torchrun --no-python --nproc-per-node N solve_biomath …` or any
+// launcher that sets RANK, WORLD_SIZE and LOCAL_RANK; without them the drivers run on one GPU as before.
+// The exchange goes through small files in a directory all ranks of the node can see (MSGPU_RENDEZVOUS_DIR,
+// default /tmp/msgpu-rdzv-<parent pid>-<MASTER_PORT>): written to a temporary name and renamed, so a
+// reader never sees a partial file.  Everything on the data path itself is NCCL / NVLink (csrc/comm.cu).
+#pragma once
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <filesystem>
+#include <fstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace ms {
+
+class Distributed {
+ public:
+  int rank = 0, world = 1, local_rank = 0;
+
+  static Distributed from_env() {
+    Distributed d;
+    const char* r = std::getenv("RANK");
+    const char* w = std::getenv("WORLD_SIZE");
+    const char* l = std::getenv("LOCAL_RANK");
+    if (r && w && std::atoi(w) > 1) {
+      d.rank = std::atoi(r);
+      d.world = std::atoi(w);
+      d.local_rank = l ? std::atoi(l) : d.rank;
+      const char* dir = std::getenv("MSGPU_RENDEZVOUS_DIR");
+      const char* port = std::getenv("MASTER_PORT");
+      d.dir_ = dir ? dir
+                   : "/tmp/msgpu-rdzv-" + std::to_string(static_cast<long>(getppid())) + "-" + (port ? port : "0");
+      std::error_code ec;
+      std::filesystem::create_directories(d.dir_, ec);
+    }
+    return d;
+  }
+  bool active() const { return world > 1; }
+
+  // allgather of one fixed-size blob per rank: all[r*bytes .. (r+1)*bytes) = blob of rank r
+  void allgather(const void* mine, size_t bytes, std::vector<unsigned char>& all, double timeout_s = 300.0) {
+    all.assign(bytes * world, 0);
+    if (!active()) {
+      std::copy(static_cast<const unsigned char*>(mine), static_cast<const unsigned char*>(mine) + bytes, all.begin());
+      return;
+    }
+    const std::string tag = dir_ + "/x" + std::to_string(counter_++) + ".";
+    {
+      const std::string tmp = tag + std::to_string(rank) + ".tmp", fin = tag + std::to_string(rank);
+      std::ofstream out(tmp, std::ios::binary);
+      out.write(static_cast<const char*>(mine), static_cast<std::streamsize>(bytes));
+      out.close();
+      std::filesystem::rename(tmp, fin);
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < world; ++r) {
+      const std::string f = tag + std::to_string(r);
+      for (;;) {
+        std::error_code ec;
+        if (std::filesystem::exists(f, ec) && std::filesystem::file_size(f, ec) == bytes) break;
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s)
+          throw std::runtime_error("rendezvous timed out waiting for rank " + std::to_string(r) + " (" + f + ")");
+        std::this_thread::sleep_for(std::chrono::milliseconds(2));
+      }
+      std::ifstream in(f, std::ios::binary);
+      in.read(reinterpret_cast<char*>(all.data() + bytes * r), static_cast<std::streamsize>(bytes));
+    }
+    // everybody has written exchange c, so everybody has finished reading exchange c-1: drop this rank's old file
+    if (!last_file_.empty()) {
+      std::error_code ec;
+      std::filesystem::remove(last_file_, ec);
+    }
+    last_file_ = tag + std::to_string(rank);
+  }
+  // blob of rank `root` to everybody
+  void broadcast(void* blob, size_t bytes, int root = 0) {
+    std::vector<unsigned char> all;
+    allgather(blob, bytes, all);
+    std::copy(all.begin() + bytes * root, all.begin() + bytes * (root + 1), static_cast<unsigned char*>(blob));
+  }
+  void barrier() {
+    unsigned char b = 1;
+    std::vector<unsigned char> all;
+    allgather(&b, 1, all);
+  }
+  // Ends the exchange: after a last barrier every other rank leaves a marker and goes; rank 0 waits for the
+  // markers (nobody reads anything any more) and removes the directory.
+  void finalize() {
+    if (!active()) return;
+    barrier();
+    if (rank != 0) {
+      std::ofstream(dir_ + "/bye." + std::to_string(rank)) << 1;
+      return;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 1; r < world; ++r) {
+      std::error_code ec;
+      while (!std::filesystem::exists(dir_ + "/bye." + std::to_string(r), ec) &&
+             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < 30.0)
+        std::this_thread::sleep_for(std::chrono::milliseconds(2));
+    }
+    std::error_code ec;
+    std::filesystem::remove_all(dir_, ec);
+  }
+
+ private:
+  std::string dir_, last_file_;
+  unsigned long counter_ = 0;
+};
+
+// the one per process: every Manager of a sweep shares it, so exchange names never repeat
+inline Distributed& distributed() {
+  static Distributed d = Distributed::from_env();
+  return d;
+}
+
+}  // namespace ms

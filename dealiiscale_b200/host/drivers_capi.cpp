@@ -30,6 +30,32 @@ extern "C" {
 
 const char* msdrv_last_error() { return g_error.c_str(); }
 
+// ---- the out-of-band exchange of the multi-process drivers (distributed.h): host-only self test --------
+// Reads RANK / WORLD_SIZE / MSGPU_RENDEZVOUS_DIR; every rank contributes a blob derived from its rank and
+// checks what it gets back from allgather, broadcast and barrier.  Returns the world size, -1 on a mismatch.
+int msdrv_rendezvous_selftest(int rounds) {
+  return guarded([&] {
+    ms::Distributed& d = ms::distributed();
+    for (int it = 0; it < rounds; ++it) {
+      unsigned char mine[128];
+      for (int i = 0; i < 128; ++i) mine[i] = static_cast<unsigned char>(7 * d.rank + 3 * i + it);
+      std::vector<unsigned char> all;
+      d.allgather(mine, sizeof mine, all);
+      for (int r = 0; r < d.world; ++r)
+        for (int i = 0; i < 128; ++i)
+          if (all[128 * r + i] != static_cast<unsigned char>(7 * r + 3 * i + it)) return -1;
+      unsigned char id[64];
+      for (int i = 0; i < 64; ++i) id[i] = d.rank == 1 % d.world ? static_cast<unsigned char>(200 - i + it) : 0;
+      d.broadcast(id, sizeof id, 1 % d.world);
+      for (int i = 0; i < 64; ++i)
+        if (id[i] != static_cast<unsigned char>(200 - i + it)) return -1;
+      d.barrier();
+    }
+    d.finalize();
+    return d.world;
+  });
+}
+
 // ---- solution files (output.h): host-only, no device involved -----------------------------------
 // format 0 = DataOut::write_gnuplot, 1 = DataOut::write_vtk; nodal[(nc+1)^2] in the reference numbering of the mesh kind
 int msdrv_write_solution(const char* path, int format, int mesh_kind, int cells_per_axis, const double* nodal,

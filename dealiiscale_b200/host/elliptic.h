@@ -173,22 +173,25 @@ class Manager {
                       std::to_string(macro_solver.mesh.n), sci3(r.mL2), sci3(r.mH1), sci3(r.ML2), sci3(r.MH1)});
     return format_table({"cycle", "cells", "dofs", "mL2", "mH1", "ML2", "MH1"}, rows);
   }
-  void output_results() {  // manager.cpp:79-88
+  void output_results() {  // manager.cpp:79-88; several ranks: rank 0 writes the table and the macro file
     if (ct_file_name.empty()) return;
-    {
+    if (distributed().rank == 0) {
       std::ofstream out(ct_file_name, std::ios::app);
       out << convergence_table();
     }
     if (solution_files_enabled()) patch_and_write_solutions();
   }
   // manager.cpp:91-131.  NB micro-error.gpl holds (computed - projected exact) of the middle grid and, like the
-  // reference, this leaves the PROJECTED EXACT solutions in the micro solver.
+  // reference, this leaves the PROJECTED EXACT solutions in the micro solver.  The rank that owns the middle
+  // grid writes the three micro files.
   void patch_and_write_solutions() {
     ensure_directory(output_dir);
-    write_gnuplot_file(output_dir + "/macro-solution.gpl", macro_solver.mesh, macro_solver.solution, "solution");
+    if (distributed().rank == 0)
+      write_gnuplot_file(output_dir + "/macro-solution.gpl", macro_solver.mesh, macro_solver.solution, "solution");
+    const int some_int = static_cast<int>(micro_solver.get_num_grids() / 2);
+    if (!micro_solver.owns(some_int)) return;
     MacroMesh micro_mesh;
     micro_mesh.build(MSGPU_MESH_REFINE_GLOBAL, micro_solver.cells_per_axis());
-    const int some_int = static_cast<int>(micro_solver.get_num_grids() / 2);
     const std::vector<double> computed = micro_solver.solution(some_int);
     write_gnuplot_file(output_dir + "/micro-computed.gpl", micro_mesh, computed, "solution");
     std::printf("Exact micro-solution set\n");
@@ -215,7 +218,8 @@ class Manager {
   void fixed_point_iterate() {  // manager.cpp:53-58
     macro_solver.run();
     micro_solver.run();
-    std::printf("\t %d CG iterations to convergence (micro)\n", micro_solver.iterations.back());
+    if (!micro_solver.iterations.empty())  // the last grid of this rank (micro.cpp:181 prints the last grid's count)
+      std::printf("\t %d CG iterations to convergence (micro)\n", micro_solver.iterations.back());
   }
   void compute_errors(double& old_residual, double& residual) {  // manager.cpp:60-77
     CycleRecord r;

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/msgpu.h"
+#include "distributed.h"
 #include "macro_fem.h"
 #include "prm.h"
 
@@ -45,16 +46,46 @@ class MicroSolver {
   void set_scalars(const std::vector<double>& v) { check(msgpu_set_scalars(ctx_, v.data(), static_cast<int>(v.size()))); }
 
   // ---- the reference interface ----
+  // All N macro support points.  With several ranks (distributed.h) this process keeps the contiguous block
+  // [k0, k1) of msgpu_partition; every per-grid array the MACRO side sees (coupling integrals, error norms)
+  // still has N entries, allgathered over NCCL / NVLink.
   void set_grid_locations(const std::vector<std::array<double, 2>>& locations) {
-    num_grids_ = static_cast<int>(locations.size());
-    check(msgpu_set_grid_locations(ctx_, &locations[0][0], num_grids_));
+    n_total_ = static_cast<int>(locations.size());
+    Distributed& d = distributed();
+    k0_ = 0;
+    k1_ = n_total_;
+    if (d.active()) check(msgpu_partition(n_total_, d.world, d.rank, &k0_, &k1_));
+    num_grids_ = k1_ - k0_;
+    check(msgpu_set_grid_locations(ctx_, &locations[k0_][0], num_grids_));
   }
-  void setup() { check(msgpu_setup(ctx_)); }
+  void setup() {
+    Distributed& d = distributed();
+    if (d.active()) {  // ncclGetUniqueId on rank 0 -> everybody -> ncclCommInitRank
+      char id[128] = {};
+      if (d.rank == 0) check(msgpu_comm_unique_id(id));
+      d.broadcast(id, sizeof id, 0);
+      check(msgpu_comm_init(ctx_, id, d.rank, d.world, n_total_, k0_));
+    }
+    check(msgpu_setup(ctx_));
+    const char* nccl_only = std::getenv("MSGPU_NCCL_ALLGATHER");
+    if (d.active() && d.world <= 8 && !(nccl_only && nccl_only[0] == '1')) {
+      // fused coupling + allgather over peer memory (csrc/comm.cu): exchange the 64-byte IPC handles
+      unsigned char mine[64];
+      check(msgpu_comm_p2p_export(ctx_, mine));
+      std::vector<unsigned char> all;
+      d.allgather(mine, sizeof mine, all);
+      check(msgpu_comm_p2p_attach(ctx_, all.data()));
+    }
+  }
+  int first_grid() const { return k0_; }           // global index of this rank's first micro system
+  int n_total() const { return n_total_; }
+  bool owns(int k) const { return k >= k0_ && k < k1_; }
   void set_macro_solution(const std::vector<double>* u, const std::vector<double>* w = nullptr) {
     macro_u_ = u;
     macro_w_ = w;
   }
-  unsigned int get_num_grids() const { return num_grids_; }
+  unsigned int get_num_grids() const { return n_total_; }  // all ranks' grids, as the macro solver counts them
+  unsigned int get_num_local_grids() const { return num_grids_; }
   int n_dofs() const { return n_dofs_; }
   int cells_per_axis() const { return cells_; }
 
@@ -79,20 +110,24 @@ class MicroSolver {
   }
   // MacroSolver::compute_microscopic_contribution reads these
   void coupling(std::vector<double>& c0, std::vector<double>* c1 = nullptr) {
-    c0.assign(num_grids_, 0.0);
-    std::vector<double> dummy(num_grids_);
-    if (c1) c1->assign(num_grids_, 0.0);
+    c0.assign(n_total_, 0.0);
+    std::vector<double> dummy(n_total_);
+    if (c1) c1->assign(n_total_, 0.0);
     check(msgpu_coupling(ctx_, c0.data(), c1 ? c1->data() : dummy.data()));
   }
   // per-grid norms; the aggregation over the macro mesh is done by the caller (micro.cpp:206-214)
   void grid_errors(std::vector<double>& l2, std::vector<double>& h1) {
-    l2.assign(num_grids_, 0.0);
-    h1.assign(num_grids_, 0.0);
-    check(msgpu_errors(ctx_, l2.data(), h1.data()));
+    std::vector<double> local(2 * static_cast<size_t>(num_grids_)), all(2 * static_cast<size_t>(n_total_));
+    check(msgpu_errors(ctx_, local.data(), local.data() + num_grids_));
+    check(msgpu_comm_allgather(ctx_, local.data(), all.data(), 2));  // a copy on one rank
+    l2.assign(all.begin(), all.begin() + n_total_);
+    h1.assign(all.begin() + n_total_, all.end());
   }
   void grid_residuals(std::vector<double>& l2) {
-    l2.assign(num_grids_, 0.0);
-    check(msgpu_residuals(ctx_, l2.data()));
+    std::vector<double> local(num_grids_);
+    l2.assign(n_total_, 0.0);
+    check(msgpu_residuals(ctx_, local.data()));
+    check(msgpu_comm_allgather(ctx_, local.data(), l2.data(), 1));
   }
   void compute_all_errors(const MacroMesh& macro_mesh, int q, double& l2_error, double& h1_error) {
     std::vector<double> l2, h1;
@@ -108,14 +143,15 @@ class MicroSolver {
   // micro.cpp:224-234, bio micro.cpp:381-391, rho_solver.cpp:353-359 (t: parabolic only)
   void set_exact_solution(double t = 0.0) { check(msgpu_set_exact_solution(ctx_, t)); }
   // `solutions` of the reference (micro.h:97), reference DoF numbering
+  // k: global grid index; the grid must live on this rank (owns(k))
   std::vector<double> solution(int k) {
     std::vector<double> out(n_dofs_);
-    check(msgpu_get_solutions(ctx_, k, k + 1, out.data()));
+    check(msgpu_get_solutions(ctx_, k - k0_, k - k0_ + 1, out.data()));
     return out;
   }
   void solutions_range(int k0, int k1, std::vector<double>& out) {
     out.assign(static_cast<size_t>(k1 - k0) * n_dofs_, 0.0);
-    check(msgpu_get_solutions(ctx_, k0, k1, out.data()));
+    check(msgpu_get_solutions(ctx_, k0 - k0_, k1 - k0_, out.data()));
   }
   void all_solutions(std::vector<double>& out) {
     out.assign(static_cast<size_t>(num_grids_) * n_dofs_, 0.0);
@@ -145,10 +181,11 @@ class MicroSolver {
  private:
   msgpu_ctx* ctx_ = nullptr;
   int problem_, cells_, n_dofs_ = 0, num_grids_ = 0, macro_fields_ = 0;
+  int n_total_ = 0, k0_ = 0, k1_ = 0;  // all grids / this rank's block
   const std::vector<double>*macro_u_ = nullptr, *macro_w_ = nullptr;
   void push_macro() {
     if (!macro_u_) throw std::runtime_error("set_macro_solution was not called");
-    check(msgpu_set_macro_solution(ctx_, macro_u_->data(), macro_w_ ? macro_w_->data() : nullptr));
+    check(msgpu_set_macro_solution(ctx_, macro_u_->data() + k0_, macro_w_ ? macro_w_->data() + k0_ : nullptr));
   }
   void check(int rc) {
     if (rc != MSGPU_OK) throw std::runtime_error(std::string("msgpu: ") + msgpu_last_error(ctx_));

@@ -234,9 +234,9 @@ class TimeManager {
     }
     return format_table({"iteration", "time", "cells", "dofs", "mL2", "ML2", "mH1", "MH1"}, rows);
   }
-  // time_manager.cpp:92-109, called after every time step (:69)
+  // time_manager.cpp:92-109, called after every time step (:69); grid 0 and the macro solution live on rank 0
   void write_plot() {
-    if (ct_file_name.empty() || !solution_files_enabled()) return;
+    if (ct_file_name.empty() || !solution_files_enabled() || distributed().rank != 0) return;
     ensure_directory(output_dir);
     write_vtk_file(output_dir + "/micro-solution" + int_to_string(it, 3) + ".vtk", micro_mesh(), rho_solver.solution(0),
                    "solution");
@@ -245,36 +245,42 @@ class TimeManager {
   }
   void output_results() {  // time_manager.cpp:111-143
     if (ct_file_name.empty()) return;
-    {
+    const bool root = distributed().rank == 0;
+    if (root) {
       std::ofstream out(ct_file_name, std::ios::app);
       out << convergence_table();
     }
     if (!solution_files_enabled()) return;
     ensure_directory(output_dir);
-    write_gnuplot_file(output_dir + "/final_macro_solution.gpl", pi_solver.mesh, pi_solver.solution, "solution");
+    if (root)
+      write_gnuplot_file(output_dir + "/final_macro_solution.gpl", pi_solver.mesh, pi_solver.solution, "solution");
     const unsigned int index = rho_solver.get_num_grids() / 2;
-    write_gnuplot_file(output_dir + "/final_micro_solution.gpl", micro_mesh(), rho_solver.solution(index), "solution");
+    if (rho_solver.owns(index))
+      write_gnuplot_file(output_dir + "/final_micro_solution.gpl", micro_mesh(), rho_solver.solution(index), "solution");
     std::vector<std::array<double, 2>> dof_locations;
     pi_solver.get_dof_locations(dof_locations);
     patch_micro_solutions(dof_locations);
   }
   // RhoSolver::patch_micro_solutions (rho_solver.cpp:240-283): every micro solution drawn on a small copy of the
-  // micro mesh centred at its macro point, all into one gnuplot file
+  // micro mesh centred at its macro point, all into one gnuplot file (several ranks: one file per rank,
+  // patched_micro_solution.<rank>.gpl, each holding the grids that rank owns)
   void patch_micro_solutions(const std::vector<std::array<double, 2>>& locations) {
-    std::ofstream output(output_dir + "/patched_micro_solution.gpl");
+    const Distributed& d = distributed();
+    std::ofstream output(output_dir + (d.active() ? "/patched_micro_solution." + std::to_string(d.rank) + ".gpl"
+                                                  : std::string("/patched_micro_solution.gpl")));
     const double side_length = std::pow(static_cast<double>(locations.size()), 0.5);
     const double size = 1.0 / (static_cast<int>(side_length) - 1);  // get_micro_grid_size
     const double micro_size = 2 * size;
     const MacroMesh& mm = micro_mesh();
     std::vector<double> all;
-    rho_solver.all_solutions(all);
-    const size_t n = rho_solver.n_dofs();
+    rho_solver.all_solutions(all);  // this rank's grids
+    const size_t n = rho_solver.n_dofs(), first = rho_solver.first_grid();
     std::vector<double> one(n);
-    for (size_t i = 0; i < locations.size(); ++i) {
+    for (size_t i = 0; i < rho_solver.get_num_local_grids(); ++i) {
       std::copy(all.begin() + i * n, all.begin() + (i + 1) * n, one.begin());
       Placement pl;
-      pl.x0 = -0.5 * micro_size + locations[i][0];
-      pl.y0 = -0.5 * micro_size + locations[i][1];
+      pl.x0 = -0.5 * micro_size + locations[first + i][0];
+      pl.y0 = -0.5 * micro_size + locations[first + i][1];
       pl.width = micro_size;
       write_gnuplot(output, mm, one, "solution", pl);
     }

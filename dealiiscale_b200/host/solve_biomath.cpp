@@ -1,6 +1,8 @@
 // solve_biomath [input.prm [macro_refinement [micro_refinement [num_threads]]]] — same command line
 // and timing line as the reference (manufactured.cpp:39-90).  num_threads is accepted for
-// compatibility; the micro path runs on the GPU.
+// compatibility; the micro path runs on the GPU.  Under a launcher that sets RANK / WORLD_SIZE / LOCAL_RANK
+// (e.g. `torchrun --no-python --nproc-per-node 8 solve_biomath input/biocase.prm 6 6`) the macro points are
+// sharded over one process per GPU (distributed.h); rank 0 prints and writes the table.
 #include <chrono>
 #include <ctime>
 #include <regex>
@@ -14,14 +16,19 @@ int main(int argc, char* argv[]) {
   if (argc >= 3) macro_refinement = std::stoi(argv[2]);
   if (argc >= 4) micro_refinement = std::stoi(argv[3]);
   if (argc >= 5) num_threads = std::stoi(argv[4]);
+  ms::Distributed& dist = ms::distributed();
+  if (dist.rank != 0 && !std::freopen("/dev/null", "w", stdout)) return 3;
   const auto wall0 = std::chrono::steady_clock::now();
   const std::clock_t cpu0 = std::clock();
   const std::string output_path = "results/out.txt";
-  { std::ofstream truncate(output_path, std::ios::trunc); }
+  if (dist.rank == 0) { std::ofstream truncate(output_path, std::ios::trunc); }
   try {
-    ms::bio::Manager manager(1u << macro_refinement, 1u << micro_refinement, input_path, output_path, num_threads);
+    ms::bio::Manager manager(1u << macro_refinement, 1u << micro_refinement, input_path, output_path, num_threads,
+                             dist.active() ? dist.local_rank : -1);
+    if (const char* e = std::getenv("MSGPU_CYCLE_LIMIT")) manager.cycle_limit = std::atoi(e);  // extension: stop after K cycles
     manager.setup();
     manager.run();
+    dist.finalize();
   } catch (const std::exception& e) {
     std::fprintf(stderr, "solve_biomath: %s\n", e.what());
     return 2;
@@ -30,7 +37,7 @@ int main(int argc, char* argv[]) {
   const double cpu = double(std::clock() - cpu0) / CLOCKS_PER_SEC;
   std::printf("Results: 'macro_refinement', 'micro_refinement', 'num_threads', 'wall_time', 'cpu_time'\n");
   std::printf("%d, %d, %d, %.3f, %.3f\n", macro_refinement, micro_refinement, num_threads, wall, cpu);
-  if (num_threads != 0) {
+  if (num_threads != 0 && dist.rank == 0) {
     std::smatch m;
     const std::string id = std::regex_search(input_path, m, std::regex("input/(.+).prm")) ? m[1].str() : "run";
     std::ofstream t("results/" + id + "_timings.txt", std::ios::app);

@@ -16,13 +16,17 @@ int main(int argc, char* argv[]) {
   std::smatch m;
   const std::string id = std::regex_search(input_path, m, std::regex("input/(.+).prm")) ? m[1].str() : "run";
   const std::string output_path = "results/" + id + "_convergence_table.txt";
-  { std::ofstream truncate(output_path, std::ios::trunc); }
+  ms::Distributed& dist = ms::distributed();  // one process per GPU when RANK / WORLD_SIZE / LOCAL_RANK are set
+  if (dist.rank != 0 && !std::freopen("/dev/null", "w", stdout)) return 3;
+  if (dist.rank == 0) { std::ofstream truncate(output_path, std::ios::trunc); }
   try {
     for (unsigned int i = 2; i < 6; i++) {
-      ms::elliptic::Manager manager(i - 1, i, input_path, output_path);
+      ms::elliptic::Manager manager(i - 1, i, input_path, output_path, dist.active() ? dist.local_rank : -1);
+      if (const char* e = std::getenv("MSGPU_CYCLE_LIMIT")) manager.cycle_limit = std::atoi(e);  // extension: stop after K cycles
       manager.setup();
       manager.run();
     }
+    dist.finalize();
   } catch (const std::exception& e) {
     std::fprintf(stderr, "solve_elliptic: %s\n", e.what());
     return 2;

@@ -13,15 +13,19 @@ int main(int argc, char* argv[]) {
   std::smatch m;
   const std::string id = std::regex_search(input_path, m, std::regex("input/(.+).prm")) ? m[1].str() : "run";
   const std::string output_path = "results/" + id + "_convergence_table.txt";
-  { std::ofstream truncate(output_path, std::ios::trunc); }
+  ms::Distributed& dist = ms::distributed();  // one process per GPU when RANK / WORLD_SIZE / LOCAL_RANK are set
+  if (dist.rank != 0 && !std::freopen("/dev/null", "w", stdout)) return 3;
+  if (dist.rank == 0) { std::ofstream truncate(output_path, std::ios::trunc); }
   try {
     for (int i = 0; i < levels; i++) {
       const auto h_inv = static_cast<unsigned int>(std::round(8 * std::pow(2, i / 2.)));
       const auto t_inv = static_cast<unsigned int>(std::round(4 * std::pow(2, i)));
-      ms::parabolic::TimeManager manager(h_inv, h_inv, t_inv, input_path, output_path);
+      ms::parabolic::TimeManager manager(h_inv, h_inv, t_inv, input_path, output_path,
+                                         dist.active() ? dist.local_rank : -1);
       manager.setup();
       manager.run();
     }
+    dist.finalize();
   } catch (const std::exception& e) {
     std::fprintf(stderr, "solve_parabolic: %s\n", e.what());
     return 2;

@@ -10,7 +10,7 @@ import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from helpers import BIO, INPUT, MESH_SUBDIVIDED, Emul, configure_bio
+from helpers import BIO, INPUT, MESH_SUBDIVIDED, ROOT, Emul, configure_bio
 from dealiiscale_b200.capi import partition
 from dealiiscale_b200.parallel import MacroSharding
 from dealiiscale_b200.prm import BioData
@@ -74,3 +74,20 @@ def test_partition_covers_everything_once():
             sh = MacroSharding(n_total, r, world)
             assert (sh.k0, sh.k1) == (k0, k1) and sh.n_local <= sh.block
         assert seen == list(range(n_total))
+
+
+def test_cpp_driver_rendezvous_between_processes(tmp_path):
+    """host/distributed.h: the file-based exchange the multi-process C++ drivers use for the NCCL unique id and the
+    peer-memory handles (allgather, broadcast, barrier, clean-up), three processes, no GPU involved."""
+    import subprocess
+    import sys
+
+    code = ("import ctypes, os, sys; "
+            f"lib = ctypes.CDLL({os.path.join(ROOT, 'dealiiscale_b200', '_build', 'libmsdrivers.so')!r}); "
+            "sys.exit(0 if lib.msdrv_rendezvous_selftest(5) == int(os.environ['WORLD_SIZE']) else 1)")
+    rdzv = os.path.join(tmp_path, "rdzv")
+    procs = [subprocess.Popen([sys.executable, "-c", code],
+                              env=dict(os.environ, RANK=str(r), WORLD_SIZE="3", LOCAL_RANK=str(r),
+                                       MSGPU_RENDEZVOUS_DIR=rdzv)) for r in range(3)]
+    assert [p.wait(timeout=120) for p in procs] == [0, 0, 0]
+    assert not os.path.exists(rdzv)  # rank 0 removed the exchange directory after the last barrier
