@@ -135,7 +135,7 @@ def test_cli_binaries_run_and_write_the_table(tmp_path):
     assert "Results: 'macro_refinement', 'micro_refinement', 'num_threads', 'wall_time', 'cpu_time'" in r.stdout
     table = open(os.path.join(tmp_path, "results", "out.txt")).read()
     assert table.split()[:7] == ["cycle", "cells", "dofs", "mL2", "mH1", "ML2", "MH1"]
-    # the solution files of bio manager.cpp:125-195 (2x2 macro cells -> 9 micro grids of 3x3 cells)
+    # the solution files of bio manager.cpp:125-195 (refinements 1, 3: 2x2 macro cells -> 9 micro grids of 8x8 cells)
     res = os.path.join(tmp_path, "results")
     for f in ["u-solution.vtk", "w-solution.vtk", "micro-error.vtk", "micro-exact.vtk", "micro-solutions/grid_locations.txt"] \
             + [f"micro-solutions/v-solution-{k}.vtk" for k in range(9)]:
@@ -144,7 +144,7 @@ def test_cli_binaries_run_and_write_the_table(tmp_path):
     from test_output_files import parse_vtk
 
     pts, cells, types, name, data = parse_vtk(os.path.join(res, "micro-exact.vtk"))
-    assert name == "v" and len(cells) == 9 and np.isfinite(data).all()
+    assert name == "v" and len(cells) == 64 and np.isfinite(data).all()
     # linear.prm has a manufactured solution: the projected exact solution minus the computed one is small
     _, _, _, _, err = parse_vtk(os.path.join(res, "micro-error.vtk"))
     assert np.abs(err).max() < 0.5 * np.abs(data).max()
