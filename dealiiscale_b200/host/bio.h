@@ -134,17 +134,23 @@ class MacroSolver {
   void solve() {  // macro.cpp:194-202
     old_sol_u = sol_u;
     old_sol_w = sol_w;
-    solve_cg(system_matrix_u, sol_u, system_rhs_u, 10000, 1e-12);
-    solve_cg(system_matrix_w, sol_w, system_rhs_w, 10000, 1e-12);
+    if (micro->solves_macro_here()) {
+      solve_cg(system_matrix_u, sol_u, system_rhs_u, 10000, 1e-12);
+      solve_cg(system_matrix_w, sol_w, system_rhs_w, 10000, 1e-12);
+    }
+    micro->share_macro_solution(sol_u, &sol_w);
   }
   void assemble_and_solve() {
     if (on_device) {
       compute_microscopic_contribution();  // integrals stay on the device; host copies are for the records
       old_sol_u = sol_u;
       old_sol_w = sol_w;
-      micro->macro_solve(1e-12, 10000, true);
-      micro->macro_get_solution(0, sol_u);
-      micro->macro_get_solution(1, sol_w);
+      if (micro->solves_macro_here()) {
+        micro->macro_solve(1e-12, 10000, true);
+        micro->macro_get_solution(0, sol_u);
+        micro->macro_get_solution(1, sol_w);
+      }
+      micro->share_macro_solution(sol_u, &sol_w);
       return;
     }
     assemble_system();

@@ -84,14 +84,18 @@ class MacroSolver {
     apply_boundary_values(boundary_values, system_matrix, solution, system_rhs);
   }
   void solve() {  // macro.cpp:108-114
-    last_iterations = solve_cg(system_matrix, solution, system_rhs, 1000, 1e-12);
+    if (micro->solves_macro_here()) last_iterations = solve_cg(system_matrix, solution, system_rhs, 1000, 1e-12);
+    micro->share_macro_solution(solution);
     std::printf("\t %d CG iterations to convergence (macro)\n", last_iterations);
   }
   void run() {  // macro.cpp:177-181
     if (on_device) {
       compute_microscopic_contribution();  // leaves the integrals on the device; the host copy is for the records
-      last_iterations = micro->macro_solve(1e-12, 1000, true)[0];
-      micro->macro_get_solution(0, solution);
+      if (micro->solves_macro_here()) {
+        last_iterations = micro->macro_solve(1e-12, 1000, true)[0];
+        micro->macro_get_solution(0, solution);
+      }
+      micro->share_macro_solution(solution);
       std::printf("\t %d CG iterations to convergence (macro)\n", last_iterations);
       return;
     }

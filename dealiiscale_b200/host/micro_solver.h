@@ -175,6 +175,17 @@ class MicroSolver {
     check(msgpu_macro_solve(ctx_, tol, max_it, adopt ? 1 : 0, its.data()));
     return its;
   }
+  // The macro step on several GPUs.  Default: every rank solves the (tiny) macro system itself from the
+  // allgathered integrals.  MSGPU_MACRO_BROADCAST=1: rank 0 alone solves and the solution is broadcast with
+  // ncclBroadcast (BASELINE.json north_star; msgpu_broadcast_macro also places this rank's block on the device).
+  static bool macro_broadcast() {
+    const char* e = std::getenv("MSGPU_MACRO_BROADCAST");
+    return distributed().active() && e && e[0] == '1';
+  }
+  static bool solves_macro_here() { return !macro_broadcast() || distributed().rank == 0; }
+  void share_macro_solution(std::vector<double>& u, std::vector<double>* w = nullptr) {
+    if (macro_broadcast()) check(msgpu_broadcast_macro(ctx_, u.data(), w ? w->data() : nullptr, 0));
+  }
   msgpu_ctx* context() { return ctx_; }
   std::vector<int> iterations;  // CG steps of every grid in the last solve
 

@@ -114,14 +114,17 @@ class PiSolver {
     on_device = true;
   }
   void solve() {
-    if (on_device) {
-      micro->macro_set_solution(0, solution);  // boundary values may move with t (apply_boundary_values set them)
-      micro->macro_set_rhs(0, system_rhs);
-      last_iterations = micro->macro_solve(1e-12, 10000, false)[0];
-      micro->macro_get_solution(0, solution);
-      return;
+    if (micro->solves_macro_here()) {
+      if (on_device) {
+        micro->macro_set_solution(0, solution);  // boundary values may move with t (apply_boundary_values set them)
+        micro->macro_set_rhs(0, system_rhs);
+        last_iterations = micro->macro_solve(1e-12, 10000, false)[0];
+        micro->macro_get_solution(0, solution);
+      } else {
+        last_iterations = solve_cg(system_matrix, solution, system_rhs, 10000, 1e-12);
+      }
     }
-    last_iterations = solve_cg(system_matrix, solution, system_rhs, 10000, 1e-12);
+    micro->share_macro_solution(solution);
   }
   double solution_difference() const {  // pi_solver.cpp:267-277
     std::vector<double> d(mesh.n);

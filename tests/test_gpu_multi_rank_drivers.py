@@ -50,7 +50,9 @@ def test_two_ranks_reproduce_the_single_process_run(tmp_path, name, args, table)
         pytest.skip("needs two GPUs")
     base = {"MSGPU_CYCLE_LIMIT": "4"} if name == "bio_nosol" else {}
     one, out1 = _run(str(tmp_path), name + "_1", args, 1, 0, base)
-    for tag, env in (("p2p", {}), ("nccl", {"MSGPU_NCCL_ALLGATHER": "1"}), ("hostmacro", {"MSGPU_HOST_MACRO": "1"})):
+    for tag, env in (("p2p", {}), ("nccl", {"MSGPU_NCCL_ALLGATHER": "1"}), ("hostmacro", {"MSGPU_HOST_MACRO": "1"}),
+                     ("bcast", {"MSGPU_MACRO_BROADCAST": "1"}),  # rank 0 solves the macro system, ncclBroadcast
+                     ("bcasthost", {"MSGPU_MACRO_BROADCAST": "1", "MSGPU_HOST_MACRO": "1"})):
         two, out2 = _run(str(tmp_path), f"{name}_2_{tag}", args, 2, 29700 + len(tag), dict(base, **env))
         if table:
             t1 = open(os.path.join(one, "results", table)).read()
