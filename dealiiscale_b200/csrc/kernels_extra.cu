@@ -211,9 +211,13 @@ int project_into_solutions(msgpu_ctx* ctx, const VmProgram& prog, int qe, const 
   }
   std::vector<double> pt, wt;
   gauss_legendre_unit(qe, pt, wt);
-  double *d_pt = nullptr, *d_wt = nullptr;
-  CKX(cudaMalloc(reinterpret_cast<void**>(&d_pt), qe * sizeof(double)));
-  CKX(cudaMalloc(reinterpret_cast<void**>(&d_wt), qe * sizeof(double)));
+  struct DeviceArray {  // freed on every return path
+    double* p = nullptr;
+    ~DeviceArray() { if (p) cudaFree(p); }
+  } q_pt, q_wt;
+  CKX(cudaMalloc(reinterpret_cast<void**>(&q_pt.p), qe * sizeof(double)));
+  CKX(cudaMalloc(reinterpret_cast<void**>(&q_wt.p), qe * sizeof(double)));
+  double *const d_pt = q_pt.p, *const d_wt = q_wt.p;
   CKX(cudaMemcpy(d_pt, pt.data(), qe * sizeof(double), cudaMemcpyHostToDevice));
   CKX(cudaMemcpy(d_wt, wt.data(), qe * sizeof(double), cudaMemcpyHostToDevice));
   for (int k0 = 0; k0 < N; k0 += ctx->chunk) {
@@ -258,8 +262,6 @@ int project_into_solutions(msgpu_ctx* ctx, const VmProgram& prog, int qe, const 
   int flags[4];
   CKX(cudaMemcpyAsync(flags, ctx->d_flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
   CKX(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_pt);
-  cudaFree(d_wt);
   if (flags[FLAG_CGFAIL]) {
     ctx->err = std::string("L2 projection of ") + what + " did not converge";
     return MSGPU_ERR_NO_CONVERGENCE;

@@ -639,6 +639,8 @@ int msgpu_residuals(msgpu_ctx* ctx, double* l2) {
 }
 int msgpu_set_exact_solution(msgpu_ctx* ctx, double t) {
   if (!ctx || !ctx->setup_done) return MSGPU_ERR_INVALID;
+  // the projection uses the right-hand sides as scratch: msgpu_solve is refused until the next assembly
+  if (ctx->desc.problem != MSGPU_PARABOLIC) ctx->assembled = 0;
   return set_exact_solution(ctx, t);
 }
 

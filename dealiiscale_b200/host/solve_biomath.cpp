@@ -26,9 +26,16 @@ int main(int argc, char* argv[]) {
     ms::bio::Manager manager(1u << macro_refinement, 1u << micro_refinement, input_path, output_path, num_threads,
                              dist.active() ? dist.local_rank : -1);
     if (const char* e = std::getenv("MSGPU_CYCLE_LIMIT")) manager.cycle_limit = std::atoi(e);  // extension: stop after K cycles
+    const auto t1 = std::chrono::steady_clock::now();
     manager.setup();
+    const auto t2 = std::chrono::steady_clock::now();
     manager.run();
+    const auto t3 = std::chrono::steady_clock::now();
     dist.finalize();
+    if (std::getenv("MSGPU_DRIVER_TIMING"))
+      std::printf("[timing] construct %.2f s, setup %.2f s, run + output %.2f s\n",
+                  std::chrono::duration<double>(t1 - wall0).count(), std::chrono::duration<double>(t2 - t1).count(),
+                  std::chrono::duration<double>(t3 - t2).count());
   } catch (const std::exception& e) {
     std::fprintf(stderr, "solve_biomath: %s\n", e.what());
     return 2;
