@@ -521,6 +521,12 @@ __device__ __forceinline__ double tmem_get(const TmemRow& q, int i) { return __h
 
 __host__ __device__ constexpr int tmem_pad(int m, int K) { return (m + 3 + K) & ~1; }
 
+// Bulk prefetch of `bytes` (a multiple of 16) starting at the 16-byte block that contains p into L2.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  const unsigned long long addr = reinterpret_cast<unsigned long long>(p) & ~15ull;
+  if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(addr), "r"(bytes) : "memory");
+}
+
 template <int BT, int K, bool JACOBI>
 __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
   constexpr int CW = (512 / (BT / 128)) & ~1;  // TMEM columns per warp
@@ -528,7 +534,7 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
   constexpr bool FAST = MSGPU_FAST_SCALARS;
   static_assert(BT % 128 == 0 && 14 * K + 2 <= CW, "strip must fit the TMEM columns of a thread");
   extern __shared__ __align__(16) double sm[];
-  __shared__ int s_k;
+  __shared__ int s_k, s_next;
   __shared__ uint32_t s_tmem;
   const int n = a.md.n, m = a.md.m, ld = a.md.ld;
   const int pad = tmem_pad(m, K);  // >= m + 1 + K: dead rows n..n+K-1 stay inside the guards
@@ -614,9 +620,28 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
     }
   };
 
+  // The queue is read one system ahead: while system k is being solved, the five diagonals, the right-hand
+  // side and the start vector of the NEXT system are pulled into L2 by one bulk prefetch each
+  // (cp.async.bulk.prefetch.L2, issued by one thread, no completion to wait for), so that the staging loops
+  // below find them there instead of in HBM.
+  if (tid == 0) s_next = atomicAdd(a.work_counter, 1);
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_k = atomicAdd(a.work_counter, 1);
+    if (tid == 0) {
+      s_k = s_next;
+      if (s_next < a.N) {
+        const int nx = atomicAdd(a.work_counter, 1);
+        s_next = nx;
+        if (nx < a.N) {
+          const uint32_t row_bytes = static_cast<uint32_t>(n) * 8u & ~15u;
+          const double* ng = a.diag + static_cast<size_t>(nx) * a.diag_stride;
+          if (a.diag_stride != 0)
+            for (int d = 0; d < NDIAG; ++d) l2_prefetch_bulk(ng + static_cast<size_t>(d) * ld, row_bytes);
+          l2_prefetch_bulk(a.b + static_cast<size_t>(nx) * n, row_bytes);
+          l2_prefetch_bulk(a.x + static_cast<size_t>(nx) * n, row_bytes);
+        }
+      }
+    }
     __syncthreads();
     const int k = s_k;
     if (k >= a.N) break;
