@@ -261,6 +261,15 @@ class MicroSolver:
         blob = b"".join(handles)
         self._check(self.lib.msgpu_comm_p2p_attach(self.h, blob))
 
+    def allgather(self, *local):
+        """Per-grid scalars of all ranks (1 or 2 arrays of this rank's grids -> arrays of n_total entries), e.g. the
+        error norms the stop test aggregates; ``msgpu_comm_allgather``."""
+        fields = len(local)
+        loc = np.ascontiguousarray(np.stack([np.asarray(a, dtype=np.float64) for a in local]))
+        out = np.zeros((fields, self.n_total or self.num_grids))
+        self._check(self.lib.msgpu_comm_allgather(self.h, _d(loc), _d(out), fields))
+        return out[0] if fields == 1 else tuple(out)
+
     def broadcast_macro(self, u_all, w_all=None, root=0):
         u_all = np.ascontiguousarray(u_all, dtype=np.float64)
         wp = None
