@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip(CgArgs a) {
     }
   };
 
+  bool have_matrix = false;
   for (;;) {
     __syncthreads();
     if (tid == 0) s_k = atomicAdd(a.work_counter, 1);
@@ -348,11 +349,16 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip(CgArgs a) {
     const int k = s_k;
     if (k >= a.N) break;
 
-    const double* dg = a.diag + static_cast<size_t>(k) * a.diag_stride;
-    for (int d = 0; d < NDIAG; ++d) {
-      const double* src = dg + static_cast<size_t>(d) * ld;
-      double* dst = mat + d * ms + pad;
-      for (int r = tid; r < n; r += BT) dst[r] = __ldg(src + r);
+    // one matrix shared by all systems (diag_stride == 0: the parabolic driver, many right-hand sides): it is
+    // staged once per CTA and stays resident while the CTA walks through its systems
+    if (a.diag_stride != 0 || !have_matrix) {
+      const double* dg = a.diag + static_cast<size_t>(k) * a.diag_stride;
+      for (int d = 0; d < NDIAG; ++d) {
+        const double* src = dg + static_cast<size_t>(d) * ld;
+        double* dst = mat + d * ms + pad;
+        for (int r = tid; r < n; r += BT) dst[r] = __ldg(src + r);
+      }
+      have_matrix = true;
     }
     double xx[K], gg[K], dl[K], hh[K];
     const double* bk = a.b + static_cast<size_t>(k) * n;
@@ -625,6 +631,8 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
   // (cp.async.bulk.prefetch.L2, issued by one thread, no completion to wait for), so that the staging loops
   // below find them there instead of in HBM.
   if (tid == 0) s_next = atomicAdd(a.work_counter, 1);
+  bool have_matrix = false;
+  double diag_own[JACOBI ? K : 1];
   for (;;) {
     __syncthreads();
     if (tid == 0) {
@@ -646,16 +654,22 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
     const int k = s_k;
     if (k >= a.N) break;
 
+    // One matrix shared by all systems (diag_stride == 0: the parabolic driver, many right-hand sides): staged
+    // and packed into tensor memory once per CTA, resident while the CTA walks through its systems.
+    const bool load_matrix = a.diag_stride != 0 || !have_matrix;
+    have_matrix = true;
     const double* dg = a.diag + static_cast<size_t>(k) * a.diag_stride;
     // stage M1..M4 in shared memory; M0 goes through the d buffer on its way to TMEM
-    for (int d = 1; d < NDIAG; ++d) {
-      const double* src = dg + static_cast<size_t>(d) * ld;
-      double* dst = mat + (d - 1) * ms + pad;
-      for (int r = tid; r < n; r += BT) dst[r] = __ldg(src + r);
+    if (load_matrix) {
+      for (int d = 1; d < NDIAG; ++d) {
+        const double* src = dg + static_cast<size_t>(d) * ld;
+        double* dst = mat + (d - 1) * ms + pad;
+        for (int r = tid; r < n; r += BT) dst[r] = __ldg(src + r);
+      }
+      for (int r = tid; r < n; r += BT) dv[r] = __ldg(dg + r);
     }
-    for (int r = tid; r < n; r += BT) dv[r] = __ldg(dg + r);
     __syncthreads();
-    double diag_own[JACOBI ? K : 1];
+    if (load_matrix)
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       const int r = rc0 + j;
