@@ -234,7 +234,7 @@ def workload_config(args, n_gpus):
                         + ("with ncclAllGather" if args.nccl_allgather else
                            "by the coupling kernel itself (peer-memory stores over NVLink + flag per peer)")
                         + "; e2e adds an ncclBroadcast of the macro iterate per step") if n_gpus > 1 else "single GPU",
-        "l2": "inputs larger than L2: 0.7 GB of matrix values + 1.9 GB of cell moments per step",
+        "l2": "inputs larger than L2: 0.7 GB of matrix values + 0.55 GB of cell load moments written and read per step",
     }
 
 

@@ -255,10 +255,23 @@ MSGPU_HOSTDEV void body_cell_moments_vec(const VmProgram& progF, const VmProgram
   moments_to_local(acc, stiffness_scale, a);
   const double h2 = md.h * md.h;
   double* o = cell + static_cast<size_t>(kl) * CELL_STRIDE * md.ncells + c;
+  if (MODE != MODE_GENERAL) {
+    // F is constant per system: the matrix entries and the det-weighted basis integrals are the same in every
+    // cell and the gather reads them from cell 0 (GatherArgs::uniform_stiffness) — as the specialised kernel does
+    if (c == 0) {
 #pragma unroll
-  for (int e = 0; e < 10; ++e) o[static_cast<size_t>(e) * md.ncells] = a[e];
+      for (int e = 0; e < 10; ++e) o[static_cast<size_t>(e) * md.ncells] = a[e];
 #pragma unroll
-  for (int e = 10; e < CELL_STRIDE; ++e) o[static_cast<size_t>(e) * md.ncells] = acc[e] * h2;
+      for (int e = 14; e < CELL_STRIDE; ++e) o[static_cast<size_t>(e) * md.ncells] = acc[e] * h2;
+    }
+#pragma unroll
+    for (int e = 10; e < 14; ++e) o[static_cast<size_t>(e) * md.ncells] = acc[e] * h2;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 10; ++e) o[static_cast<size_t>(e) * md.ncells] = a[e];
+#pragma unroll
+    for (int e = 10; e < CELL_STRIDE; ++e) o[static_cast<size_t>(e) * md.ncells] = acc[e] * h2;
+  }
   if (bad) *error_flag = 1;  // benign race: every writer stores the same value
 }
 
@@ -333,22 +346,25 @@ MSGPU_HOSTDEV void body_gather(const GatherArgs& a, long long gtid) {
     const int c = (uniform && (e < 10 || e >= 14)) ? 0 : cx * md.nc + cy;
     return MSGPU_LDG(cellk + static_cast<size_t>(e) * md.ncells + c);
   };
+  // the parabolic driver and the L2 projections only want the load vector: the matrix is shared and built
+  // on the host, so the ten matrix entries and the four weights of a cell are not even read
+  const bool want_matrix = a.diag != nullptr, want_jw = a.jw != nullptr;
   double d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, load = 0, jw = 0;
   for (int dy = -1; dy <= 0; ++dy)
     for (int dx = -1; dx <= 0; ++dx) {
       const int cx = ix + dx, cy = iy + dy;
       if (cx < 0 || cy < 0 || cx >= md.nc || cy >= md.nc) continue;
       const int v = (ix - cx) + 2 * (iy - cy);
-      d0 += C(cx, cy, sym4(v, v));
+      if (want_matrix) d0 += C(cx, cy, sym4(v, v));
       load += C(cx, cy, 10 + v);
-      jw += C(cx, cy, 14 + v);
+      if (want_jw) jw += C(cx, cy, 14 + v);
     }
   const bool right_ok = ix < md.nc, up_ok = iy < md.nc, down_ok = iy > 0, left_ok = ix > 0;
-  if (up_ok) {  // edge to (ix, iy+1)
+  if (want_matrix && up_ok) {  // edge to (ix, iy+1)
     if (left_ok) d1 += C(ix - 1, iy, 6);   // local (1,3)
     if (right_ok) d1 += C(ix, iy, 2);      // local (0,2)
   }
-  if (right_ok) {  // edge to (ix+1, iy)
+  if (want_matrix && right_ok) {  // edge to (ix+1, iy)
     if (down_ok) d3 += C(ix, iy - 1, 8);   // local (2,3)
     if (up_ok) d3 += C(ix, iy, 1);         // local (0,1)
     if (up_ok) d4 += C(ix, iy, 3);         // diagonal to (ix+1, iy+1): local (0,3)

@@ -77,7 +77,8 @@ MSGPU_HOSTDEV void body_cell_residual(const MeshDims& md, const double* __restri
 }
 
 // Load vector of a MODE_POINTS function with a qe-point rule: cell[(k*CELL_STRIDE + 10 + v)*ncells + c]
-// = sum_q f(y_q) phi_v JxW; the other entries of the cell record are zeroed (the gather adds them).
+// = sum_q f(y_q) phi_v JxW; the other entries of the cell record are left alone (a gather without matrix and
+// weight outputs, which is the only consumer, does not read them).
 MSGPU_HOSTDEV void body_cell_point_load(const VmProgram& prog, const MeshDims& md, const double* __restrict__ slots,
                                         int n_slots, int qe, const double* __restrict__ pt,
                                         const double* __restrict__ wt, int k0, int nk, double* __restrict__ cell,
@@ -107,7 +108,6 @@ MSGPU_HOSTDEV void body_cell_point_load(const VmProgram& prog, const MeshDims& m
       a3 += f * (xi * eta);
     }
   double* o = cell + static_cast<size_t>(kl) * CELL_STRIDE * md.ncells + c;
-  for (int e = 0; e < CELL_STRIDE; ++e) o[static_cast<size_t>(e) * md.ncells] = 0.0;
   o[static_cast<size_t>(10) * md.ncells] = a0;
   o[static_cast<size_t>(11) * md.ncells] = a1;
   o[static_cast<size_t>(12) * md.ncells] = a2;

@@ -344,9 +344,9 @@ int parabolic_assemble(msgpu_ctx* ctx, double dt, double t) {
     ctx->launches += launch_cell_moments(ctx->stream, mp, md, tb, ctx->d_qtab,
                                          ctx->d_qtab + static_cast<size_t>(md.q) * md.q * QTAB_STRIDE, k0, nk, 1.0,
                                          ctx->d_cell, ctx->d_flags + FLAG_JACOBIAN);
-    for (int s = 0; s < 4; ++s)
-      ctx->launches += launch_face_moments(ctx->stream, ps.point_program(ctx->pp.prog_face[s]), s, md, tb, ctx->d_q1pt,
-                                           ctx->d_q1wt, k0, nk, 0, ctx->d_face);
+    const VmProgram* faces[4];
+    for (int s = 0; s < 4; ++s) faces[s] = &ps.point_program(ctx->pp.prog_face[s]);
+    ctx->launches += launch_face_moments_all(ctx->stream, faces, md, tb, ctx->d_q1pt, ctx->d_q1wt, k0, nk, 0, ctx->d_face);
     GatherArgs g{};
     g.md = md;
     g.problem = PF_PARABOLIC;
