@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--micro-ref", type=int, default=6, help="micro refinement: 2^r cells per axis")
     ap.add_argument("--cpu-sample", type=int, default=0, help="micro systems in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precond", default="identity", choices=["identity", "jacobi", "ssor"],
+                    help="A/B only: the reference solves with PreconditionIdentity, which is what the headline number uses")
     ap.add_argument("--nccl-allgather", action="store_true",
                     help="multi-GPU: exchange the flux integrals with ncclAllGather instead of the fused peer-memory kernel")
     return ap.parse_args()
@@ -229,7 +231,7 @@ def workload_config(args, n_gpus):
                     f"path (assemble + CG from zero start + flux integrals)",
         "prm": args.prm, "micro_cells_per_axis": mc, "micro_dofs": (mc + 1) ** 2, "q_degree": 12,
         "macro_points_per_gpu": (Mc + 1) ** 2, "macro_points_total": (Mc + 1) ** 2 * n_gpus,
-        "cg": "deal.II recurrence, identity preconditioner, abs tol 1e-12, max 10000",
+        "cg": f"deal.II recurrence, {args.precond} preconditioner, abs tol 1e-12, max 10000",
         "parallelism": (f"macro points sharded over {n_gpus} GPU(s); flux integrals exchanged "
                         + ("with ncclAllGather" if args.nccl_allgather else
                            "by the coupling kernel itself (peer-memory stores over NVLink + flag per peer)")
@@ -275,6 +277,7 @@ def main():
     ms = MicroSolver(capi.BIO, data, micro_cells, device=local_rank)
     # run on torch's current stream so that torch.cuda.Event brackets exactly the launching stream
     ms.use_stream(torch.cuda.current_stream().cuda_stream)
+    ms.precond = {"identity": capi.PRECOND_IDENTITY, "jacobi": capi.PRECOND_JACOBI, "ssor": capi.PRECOND_SSOR}[args.precond]
     ms.set_grid_locations(xy_all[k0:k1])
     if distributed:
         ids = [unique_id() if rank == 0 else None]

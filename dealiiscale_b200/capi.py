@@ -15,7 +15,7 @@ OK, ERR_INVALID, ERR_PARSE, ERR_JACOBIAN, ERR_NO_CONVERGENCE, ERR_CUDA, ERR_COMM
 ELLIPTIC, BIO, PARABOLIC = 0, 1, 2
 MESH_REFINE_GLOBAL, MESH_SUBDIVIDED = 0, 1
 (FN_MAPPING, FN_JACOBIAN, FN_RHS, FN_BC, FN_SOLUTION, FN_BC_V1, FN_BC_V2, FN_BC_V3, FN_BC_V4, FN_INIT) = range(10)
-PRECOND_IDENTITY, PRECOND_JACOBI = 0, 1
+PRECOND_IDENTITY, PRECOND_JACOBI, PRECOND_SSOR = 0, 1, 2
 
 # every symbol include/msgpu.h declares
 EXPORTED = [

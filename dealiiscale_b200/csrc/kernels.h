@@ -116,7 +116,8 @@ struct CgArgs {
   double tol;
   double tol2;              // set by launch_cg: largest t with sqrt(t) <= tol
   int max_it;
-  int precond;
+  int precond;    // 0 identity, 1 Jacobi, 2 SSOR (four-colour ordering; systems that fit one SM)
+  double omega;   // SSOR relaxation parameter (deal.II default 1)
   int* iters;               // [N]
   double* res;              // [N]
   int* work_counter;        // device int, zeroed by the launcher

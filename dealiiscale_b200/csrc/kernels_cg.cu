@@ -276,8 +276,15 @@ __global__ void __launch_bounds__(BT, 1) k_cg_resident(CgArgs a) {
 //   * the off-diagonal M1[r] is loaded once for rows r and r+1,
 //   * the left / right column values slide through a 3-register window.
 // The stride between lanes is K doubles; K is odd, so 64-bit accesses stay bank-conflict free.
-template <int BT, int K, bool JACOBI>
+// PRE: 0 = PreconditionIdentity, 1 = Jacobi, 2 = SSOR.  The SSOR sweeps run in the four-colour ordering of the
+// lattice (colour = parity of (ix, iy)): in a 9-point stencil no two nodes of one colour are coupled, so a sweep is
+// four fully parallel stages instead of n sequential updates — M = (D/w + L)(D/w)^-1 (D/w + U)/(2 - w) with L / U
+// the couplings to lower / higher colours, symmetric positive definite like the lexicographic SSOR it replaces.
+// Vertical neighbours of a node of colour c have colour c^2, horizontal ones c^1, diagonal ones c^3.
+template <int BT, int K, int PRE>
 __global__ void __launch_bounds__(BT, 1) k_cg_strip(CgArgs a) {
+  constexpr bool JACOBI = PRE == 1;
+  constexpr bool SSOR = PRE == 2;
   static_assert(K % 2 == 1, "odd strip length keeps the shared-memory accesses conflict free");
   extern __shared__ __align__(16) double sm[];
   __shared__ int s_k;
@@ -289,6 +296,14 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip(CgArgs a) {
   double* const red = sm + NDIAG * ms + (n + 2 * pad);
   const int tid = threadIdx.x;
   const int r0 = tid * K;
+  unsigned long long colours = 0;  // two bits per row of the strip
+  if (SSOR) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int r = r0 + j, ix = r / m, iy = r - ix * m;
+      colours |= static_cast<unsigned long long>((ix & 1) | ((iy & 1) << 1)) << (2 * j);
+    }
+  }
 
   for (int i = tid; i < NDIAG * ms; i += BT)
     if ((i % ms) < pad || (i % ms) >= pad + n) mat[i] = 0.0;
@@ -341,6 +356,51 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip(CgArgs a) {
     }
   };
 
+  // z = M^-1 g for the rows of this thread (SSOR); dv is the work space of the sweeps and holds garbage
+  // afterwards — every caller rewrites it with the new search direction behind the closing barrier
+  auto ssor_apply = [&](const double (&g_)[K], double (&z_)[K]) {
+    const double w = a.omega;
+    auto coupled = [&](int r, int c, bool lower) -> double {
+      const bool useV = lower ? ((c ^ 2) < c) : ((c ^ 2) > c);
+      const bool useH = lower ? ((c ^ 1) < c) : ((c ^ 1) > c);
+      const bool useD = lower ? ((c ^ 3) < c) : ((c ^ 3) > c);
+      double s = 0.0;
+      if (useV) s += M1[r] * dv[r + 1] + M1[r - 1] * dv[r - 1];
+      if (useH) s += M3[r] * dv[r + m] + M3[r - m] * dv[r - m];
+      if (useD)
+        s += M2[r] * dv[r + m - 1] + M2[r - (m - 1)] * dv[r - (m - 1)] + M4[r] * dv[r + m + 1] +
+             M4[r - (m + 1)] * dv[r - (m + 1)];
+      return s;
+    };
+    for (int c = 0; c < 4; ++c) {  // forward: (D/w + L) y = g
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const int r = r0 + j;
+        if (r < n && static_cast<int>((colours >> (2 * j)) & 3u) == c) {
+          const double y = (g_[j] - w * coupled(r, c, true)) / M0[r];
+          z_[j] = y;
+          dv[r] = y;
+        }
+      }
+      __syncthreads();
+    }
+    for (int c = 2; c >= 0; --c) {  // backward: (D/w + U) z = (D/w) y; colour 3 has nothing above it
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const int r = r0 + j;
+        if (r < n && static_cast<int>((colours >> (2 * j)) & 3u) == c) {
+          const double z = z_[j] - w * coupled(r, c, false) / M0[r];
+          z_[j] = z;
+          dv[r] = z;
+        }
+      }
+      __syncthreads();
+    }
+    const double scale = w * (2.0 - w);
+#pragma unroll
+    for (int j = 0; j < K; ++j) z_[j] = (r0 + j < n) ? z_[j] * scale : 0.0;
+  };
+
   bool have_matrix = false;
   for (;;) {
     __syncthreads();
@@ -387,7 +447,18 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip(CgArgs a) {
     double gh = 0.0;
     if (!ok) {
       __syncthreads();
-      if (JACOBI) {
+      if (SSOR) {
+        ssor_apply(gg, hh);
+        part = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const int r = r0 + j;
+          dl[j] = -hh[j];
+          part += gg[j] * hh[j];
+          if (r < n) dv[r] = dl[j];
+        }
+        gh = block_sum<BT>(part, red + 32);
+      } else if (JACOBI) {
         part = 0.0;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
@@ -429,13 +500,19 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip(CgArgs a) {
         }
         if (it >= a.max_it || res != res) break;
         double beta = gh;
-        if (JACOBI) {
+        if (JACOBI || SSOR) {
           part = 0.0;
+          if (SSOR) {
+            ssor_apply(gg, hh);
 #pragma unroll
-          for (int j = 0; j < K; ++j) {
-            const int r = r0 + j;
-            hh[j] = (r < n) ? gg[j] / M0[r] : 0.0;
-            part += gg[j] * hh[j];
+            for (int j = 0; j < K; ++j) part += gg[j] * hh[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+              const int r = r0 + j;
+              hh[j] = (r < n) ? gg[j] / M0[r] : 0.0;
+              part += gg[j] * hh[j];
+            }
           }
           gh = block_sum<BT>(part, red + 64);
           beta = gh / beta;
@@ -1219,7 +1296,7 @@ size_t resident_smem_bytes(const MeshDims& md) {
 template <int BT, int K>
 int launch_strip(cudaStream_t s, const CgArgs& a, int num_sms) {
   const size_t smem = resident_smem_bytes(a.md);
-  auto kern = a.precond == 1 ? k_cg_strip<BT, K, true> : k_cg_strip<BT, K, false>;
+  auto kern = a.precond == 2 ? k_cg_strip<BT, K, 2> : a.precond == 1 ? k_cg_strip<BT, K, 1> : k_cg_strip<BT, K, 0>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem);
@@ -1313,6 +1390,7 @@ static double squared_threshold(double tol) {
 
 int launch_cg(cudaStream_t s, const CgArgs& a_in, int num_sms, int* variant) {
   if (a_in.N == 0) return 0;
+  if (a_in.precond == 2 && !(resident_smem_bytes(a_in.md) <= 227 * 1024 && a_in.md.n <= 512 * 9)) return -2;
   CgArgs a = a_in;
   a.tol2 = squared_threshold(a.tol);
   cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
@@ -1325,7 +1403,17 @@ int launch_cg(cudaStream_t s, const CgArgs& a_in, int num_sms, int* variant) {
     const char* wide = std::getenv("MSGPU_CG_WIDE");  // "1": 1024 threads x 5 rows instead of 512 x 9
     const char* strided = std::getenv("MSGPU_CG_STRIDED");  // "1": strided row ownership (A/B measurements)
     const char* tmem = std::getenv("MSGPU_CG_TMEM");  // "0": off, "5": force the 512 x 9 shape
-    // default for the large resident sizes: matrix in tensor memory ("0" = plain strip kernel, A/B)
+    // default for the large resident sizes: matrix in tensor memory ("0" = plain strip kernel, A/B); the SSOR
+    // sweeps need all five diagonals in shared memory and live in the plain strip kernel
+    if (a.precond == 2) {
+      if (variant) *variant = 2;
+      if (n <= 32) return launch_strip<32, 1>(s, a, num_sms);
+      if (n <= 128) return launch_strip<128, 1>(s, a, num_sms);
+      if (n <= 384) return launch_strip<128, 3>(s, a, num_sms);
+      if (n <= 1280) return launch_strip<256, 5>(s, a, num_sms);
+      if (n <= 2560) return launch_strip<512, 5>(s, a, num_sms);
+      return launch_strip<512, 9>(s, a, num_sms);
+    }
     if (!(tmem && tmem[0] == '0') && !(strided && strided[0] == '1') && n > 2560) {
       if (variant) *variant = 3;
       if (n <= 256 * 17 && !(tmem && tmem[0] == '5')) return launch_strip_tmem<256, 17>(s, a, num_sms);

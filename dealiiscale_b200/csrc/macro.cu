@@ -278,6 +278,7 @@ int msgpu_macro_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int adopt, int
   a.tol = abs_tol;
   a.max_it = max_it;
   a.precond = 0;
+  a.omega = 1.0;
   a.iters = M.d_iters;
   a.res = M.d_res;
   a.work_counter = M.d_flags;

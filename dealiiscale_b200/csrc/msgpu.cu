@@ -524,8 +524,8 @@ int msgpu_assemble(msgpu_ctx* ctx) {
 
 int msgpu_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int precond, int* iters, double* final_res) {
   if (!ctx || !ctx->setup_done || !ctx->assembled) return MSGPU_ERR_INVALID;
-  if (precond != MSGPU_PRECOND_IDENTITY && precond != MSGPU_PRECOND_JACOBI)
-    return fail(ctx, MSGPU_ERR_UNSUPPORTED, "preconditioner not supported (identity and Jacobi are)");
+  if (precond != MSGPU_PRECOND_IDENTITY && precond != MSGPU_PRECOND_JACOBI && precond != MSGPU_PRECOND_SSOR)
+    return fail(ctx, MSGPU_ERR_UNSUPPORTED, "preconditioner not supported (identity, Jacobi and SSOR are)");
   CK(cudaSetDevice(ctx->device));
   const MeshDims& md = ctx->md;
   const bool shared_matrix = ctx->desc.problem == MSGPU_PARABOLIC;
@@ -543,12 +543,19 @@ int msgpu_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int precond, int* it
     a.tol = abs_tol;
     a.max_it = max_it;
     a.precond = precond;
+    a.omega = 1.0;  // PreconditionSSOR's default relaxation; MSGPU_SSOR_OMEGA in (0, 2) overrides
+    if (const char* e = std::getenv("MSGPU_SSOR_OMEGA")) {
+      const double w = std::atof(e);
+      if (w > 0.0 && w < 2.0) a.omega = w;
+    }
     a.iters = ctx->d_iters;
     a.res = ctx->d_res;
     a.work_counter = ctx->d_flags + FLAG_COUNTER;
     a.fail_flag = ctx->d_flags + FLAG_CGFAIL;
     int variant = 0;
     int l = launch_cg(ctx->stream, a, ctx->num_sms, &variant);
+    if (l == -2)
+      return fail(ctx, MSGPU_ERR_UNSUPPORTED, "SSOR preconditioning needs a system that fits one SM (at most 67 nodes per axis)");
     if (l < 0) return fail(ctx, MSGPU_ERR_CUDA, "cannot allocate the CG workspace");
     ctx->launches += l;
     ctx->cg_variant = variant;

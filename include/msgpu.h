@@ -79,7 +79,10 @@ typedef enum {
  *   parabolic : kappa, p_F, R, D                          (rho_solver.cpp:127-130)            */
 #define MSGPU_MAX_SCALARS 8
 
-typedef enum { MSGPU_PRECOND_IDENTITY = 0, MSGPU_PRECOND_JACOBI = 1 } msgpu_precond;
+/* The reference solves with PreconditionIdentity (micro.cpp:179); that is the parity default.  Jacobi and SSOR are
+ * offered for ill-conditioned maps.  SSOR sweeps run in the four-colour ordering of the lattice (a 9-point stencil
+ * never couples two nodes of one colour), relaxation 1; systems up to 67 nodes per axis. */
+typedef enum { MSGPU_PRECOND_IDENTITY = 0, MSGPU_PRECOND_JACOBI = 1, MSGPU_PRECOND_SSOR = 2 } msgpu_precond;
 
 /* ---- life cycle: MicroSolver(data, refine_level) / ~MicroSolver ------------------------- */
 int msgpu_create(msgpu_ctx** ctx, const msgpu_desc* desc);
