@@ -709,7 +709,10 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
   // below find them there instead of in HBM.
   if (tid == 0) s_next = atomicAdd(a.work_counter, 1);
   bool have_matrix = false;
-  double diag_own[JACOBI ? K : 1];
+  // Jacobi: reciprocal diagonal in the staging area of M2 (free once the matrix sits in tensor memory): no extra
+  // registers in the CG loop, a multiplication instead of a division per row
+  double* const rdiag = mat + ms + pad;
+  double d0[JACOBI ? K : 1];  // transient: the diagonal of this strip between packing and the barrier
   for (;;) {
     __syncthreads();
     if (tid == 0) {
@@ -759,10 +762,15 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
       v[4] = in ? M2[r - (m - 1)] : 0.0;
       v[5] = in ? M3[r - m] : 0.0;
       v[6] = in ? M4[r - (m + 1)] : 0.0;
-      if (JACOBI) diag_own[j] = in ? v[0] : 1.0;
+      if (JACOBI) d0[j] = in ? v[0] : 1.0;
       tmem_store_row(tbase + 14u * j, v);  // ascending j: the two surplus columns are rewritten by row j+1
     }
     __syncthreads();  // everybody has picked up M0 before d is overwritten
+    if (JACOBI && load_matrix) {
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+        if (j < nlive) rdiag[rc0 + j] = 1.0 / d0[j];  // rows past n keep the zero of the guard: z = 0 there
+    }
 
     double xx[K], gg[K], dl[K], hh[K];
     const double* bk = a.b + static_cast<size_t>(k) * n;
@@ -791,7 +799,7 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
         part = 0.0;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-          const double z = gg[j] / diag_own[j];
+          const double z = gg[j] * rdiag[rc0 + j];
           dl[j] = -z;
           part += gg[j] * z;
           if (j < nlive) dv[r0 + j] = dl[j];
@@ -841,7 +849,7 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
           part = 0.0;
 #pragma unroll
           for (int j = 0; j < K; ++j) {
-            hh[j] = gg[j] / diag_own[j];
+            hh[j] = gg[j] * rdiag[rc0 + j];
             part += gg[j] * hh[j];
           }
           gh = block_sum_tree<BT>(part, red + 64);
