@@ -95,8 +95,7 @@ class MicroSolver {
   }
   void solve() {
     iterations.assign(num_grids_, 0);
-    check(msgpu_solve(ctx_, 1e-12, problem_ == MSGPU_ELLIPTIC ? 1000 : 10000, MSGPU_PRECOND_IDENTITY, iterations.data(),
-                      nullptr));
+    check(msgpu_solve(ctx_, 1e-12, problem_ == MSGPU_ELLIPTIC ? 1000 : 10000, precond, iterations.data(), nullptr));
   }
   void run() {  // micro.cpp:218-221
     assemble_system();
@@ -188,6 +187,7 @@ class MicroSolver {
   }
   msgpu_ctx* context() { return ctx_; }
   std::vector<int> iterations;  // CG steps of every grid in the last solve
+  int precond = MSGPU_PRECOND_IDENTITY;  // the reference's choice (micro.cpp:179); Jacobi / SSOR are opt-ins
 
  private:
   msgpu_ctx* ctx_ = nullptr;
