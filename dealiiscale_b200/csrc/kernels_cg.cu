@@ -610,12 +610,23 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) 
   if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(addr), "r"(bytes) : "memory");
 }
 
+// TMEM columns a CTA of BT threads with K rows per thread allocates: the smallest power of two (>= 32) that holds
+// 14 K + 2 columns for each of the BT/128 warps of a lane quadrant.  Shapes that need less than all 512 columns
+// leave room for further CTAs on the same SM — several small systems in flight per SM, each hiding the
+// reduction latency of the others.
+__host__ __device__ constexpr int tmem_alloc_columns(int BT, int K) {
+  int need = (BT / 128) * (14 * K + 2), c = 32;
+  while (c < need) c *= 2;
+  return c;
+}
+
 template <int BT, int K, bool JACOBI>
-__global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
-  constexpr int CW = (512 / (BT / 128)) & ~1;  // TMEM columns per warp
-  constexpr int NACC = K >= 12 ? 4 : 1;        // K = 9 stays bit-identical to k_cg_strip
+__global__ void __launch_bounds__(BT, 512 / tmem_alloc_columns(BT, K)) k_cg_strip_tmem(CgArgs a) {
+  constexpr int ALLOC = tmem_alloc_columns(BT, K);
+  constexpr int CW = (ALLOC / (BT / 128)) & ~1;  // TMEM columns per warp
+  constexpr int NACC = K >= 12 ? 4 : 1;          // K = 9 stays bit-identical to k_cg_strip
   constexpr bool FAST = MSGPU_FAST_SCALARS;
-  static_assert(BT % 128 == 0 && 14 * K + 2 <= CW, "strip must fit the TMEM columns of a thread");
+  static_assert(BT % 128 == 0 && ALLOC <= 512 && 14 * K + 2 <= CW, "strip must fit the TMEM columns of a thread");
   extern __shared__ __align__(16) double sm[];
   __shared__ int s_k, s_next;
   __shared__ uint32_t s_tmem;
@@ -632,8 +643,8 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
   const int nlive = r0 < n ? (n - r0 < K ? n - r0 : K) : 0;  // rows of this strip inside the system
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(
-        static_cast<uint32_t>(__cvta_generic_to_shared(&s_tmem))));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+        static_cast<uint32_t>(__cvta_generic_to_shared(&s_tmem))), "n"(ALLOC));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
   for (int i = tid; i < 4 * ms; i += BT)
@@ -885,7 +896,7 @@ __global__ void __launch_bounds__(BT, 1) k_cg_strip_tmem(CgArgs a) {
     }
   }
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(s_tmem));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(s_tmem), "n"(ALLOC));
 }
 
 // -------------------------------------------------------------------------------------------
@@ -1325,7 +1336,14 @@ int launch_strip_tmem(cudaStream_t s, const CgArgs& a, int num_sms) {
   const size_t smem = tmem_smem_bytes(a.md, K);
   auto kern = a.precond == 1 ? k_cg_strip_tmem<BT, K, true> : k_cg_strip_tmem<BT, K, false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  long long grid = num_sms;  // one CTA per SM: each allocates all 512 TMEM columns
+  // CTAs per SM: bounded by the TMEM columns a CTA allocates (not known to the occupancy calculator), by shared
+  // memory and by registers
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem);
+  const int by_tmem = 512 / tmem_alloc_columns(BT, K);
+  if (per_sm > by_tmem) per_sm = by_tmem;
+  if (per_sm < 1) per_sm = 1;
+  long long grid = static_cast<long long>(num_sms) * per_sm;
   if (grid > a.N) grid = a.N;
   kern<<<static_cast<int>(grid), BT, smem, s>>>(a);
   return 1;
@@ -1426,6 +1444,15 @@ int launch_cg(cudaStream_t s, const CgArgs& a_in, int num_sms, int* variant) {
       if (variant) *variant = 3;
       if (n <= 256 * 17 && !(tmem && tmem[0] == '5')) return launch_strip_tmem<256, 17>(s, a, num_sms);
       if (n <= 512 * 9) return launch_strip_tmem<512, 9>(s, a, num_sms);
+    }
+    // mid sizes (1153..2304 rows, e.g. 41 x 41 nodes): 256 threads x 9 rows allocate 256 TMEM columns, two systems
+    // share an SM (3.0 instead of 4.4 ms against the plain strip kernel at 2401 systems of 2025 rows).  Below that
+    // the plain strip kernel with 3-4 CTAs per SM is the faster one (measured: 128 x 9 with 128 columns loses 12 %).
+    const char* small = std::getenv("MSGPU_CG_TMEM_SMALL");  // "0": plain strip kernel for these sizes (A/B)
+    if (!(tmem && tmem[0] == '0') && !(small && small[0] == '0') && !(strided && strided[0] == '1') && n > 128 * 9 &&
+        n <= 256 * 9) {
+      if (variant) *variant = 3;
+      return launch_strip_tmem<256, 9>(s, a, num_sms);
     }
     if (!(strided && strided[0] == '1')) {
       if (variant) *variant = 2;

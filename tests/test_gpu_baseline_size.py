@@ -116,3 +116,89 @@ def test_parabolic_at_h_inv_64():
     assert ms.stats()["cg_variant"] == TMEM_VARIANT  # one shared matrix, resident across the systems of a CTA
     ms.close()
     o.close()
+
+
+# ---- the mid sizes: 1153..2304 DoFs run the same tensor-memory kernel with 256 TMEM columns per CTA, so that two
+# ---- systems share an SM (k_cg_strip_tmem<256, 9>); up to 1152 DoFs the plain strip kernel is the faster one
+STRIP_VARIANT = 2
+
+
+@pytest.mark.parametrize("prm,micro_cells,variant", [("biocase.prm", 36, TMEM_VARIANT), ("linear.prm", 40, TMEM_VARIANT),
+                                                      ("biocase-b.prm", 47, TMEM_VARIANT), ("biocase-b.prm", 32, STRIP_VARIANT)])
+def test_bio_mid_sizes(prm, micro_cells, variant):
+    from dealiiscale_b200 import capi
+    from dealiiscale_b200.micro import MicroSolver
+    from dealiiscale_b200.prm import BioData
+
+    o = OracleBio(prm, 4, micro_cells, threads=8)   # 25 systems
+    xy = o.grid_locations()
+    u = np.sin(xy[:, 0]) * xy[:, 1] + 0.3
+    w = np.cos(xy[:, 1]) * xy[:, 0] - 0.1
+    o.micro_run(u, w)
+    ms = MicroSolver(capi.BIO, BioData(os.path.join(INPUT, prm)), micro_cells)
+    ms.set_grid_locations(xy)
+    ms.setup()
+    ms.set_macro_solution(u, w)
+    its = ms.assemble_and_solve_all()
+    assert ms.stats()["cg_variant"] == variant
+    x = ms.solutions()
+    assert max(rel_l2(x[k], o.solution(k)) for k in range(o.N)) < 1e-10
+    assert_iterations_consistent(o, its)
+    cu, cw = ms.coupling()
+    cu_o, cw_o = o.flux()
+    assert rel_l2(cu, cu_o) < 1e-10 and rel_l2(cw, cw_o) < 1e-10
+    ms.precond = capi.PRECOND_JACOBI
+    ms.zero_solutions()
+    ms.assemble_and_solve_all()
+    xj = ms.solutions()
+    ms.precond = capi.PRECOND_IDENTITY
+    ms.zero_solutions()
+    ms.assemble_and_solve_all()
+    x0 = ms.solutions()
+    assert max(rel_l2(xj[k], x0[k]) for k in range(o.N)) < 1e-8
+    ms.close()
+    o.close()
+
+
+def test_parabolic_h_inv_40_and_elliptic_refinement_5():
+    from dealiiscale_b200 import capi
+    from dealiiscale_b200.micro import MicroSolver
+    from dealiiscale_b200.prm import EllipticData, TwoPressureData
+
+    prm = "linear_time.prm"
+    for h_inv, variant in ((40, TMEM_VARIANT), (32, STRIP_VARIANT)):  # one shared matrix, resident in either kernel
+        op = OracleParabolic(prm, 5, h_inv, 16)   # 36 systems
+        xy = op.grid_locations()
+        mp = MicroSolver(capi.PARABOLIC, TwoPressureData(os.path.join(INPUT, prm)), h_inv)
+        mp.set_grid_locations(xy)
+        mp.setup()
+        dt, t = 1.0 / 16, 0.0
+        for step in range(2):
+            t += dt
+            pi = np.cos(xy[:, 0]) * xy[:, 1] + 2 + 0.1 * step
+            op.micro_step(pi, dt, t)
+            mp.set_macro_solution(pi)
+            its = mp.iterate(dt, t)
+            x = mp.solutions()
+            assert max(rel_l2(x[k], op.solution(k)) for k in range(op.N)) < 1e-10
+            assert np.abs(its - op.iters()).max() <= 1
+        assert mp.stats()["cg_variant"] == variant
+        mp.close()
+        op.close()
+
+    o = OracleElliptic("elliptic_non_linear.prm", 2, 5)
+    xy = o.grid_locations()
+    u = np.sin(xy[:, 0]) * xy[:, 1] + 0.3
+    o.micro_run(u)
+    ms = MicroSolver(capi.ELLIPTIC, EllipticData(os.path.join(INPUT, "elliptic_non_linear.prm")), 32)
+    ms.set_grid_locations(xy)
+    ms.setup()
+    ms.set_macro_solution(u)
+    its = ms.run()
+    assert ms.stats()["cg_variant"] == STRIP_VARIANT
+    x = ms.solutions()
+    assert max(rel_l2(x[k], o.solution(k)) for k in range(o.N)) < 1e-10
+    assert_iterations_consistent(o, its, unknowns=31 ** 2)
+    assert rel_l2(ms.coupling(), o.bulk()) < 1e-10
+    ms.close()
+    o.close()
