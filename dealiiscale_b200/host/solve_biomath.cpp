@@ -21,6 +21,7 @@ int main(int argc, char* argv[]) {
   const auto wall0 = std::chrono::steady_clock::now();
   const std::clock_t cpu0 = std::clock();
   const std::string output_path = "results/out.txt";
+  ms::ensure_directory("results");  // the reference expects it to exist (populate.sh links it)
   if (dist.rank == 0) { std::ofstream truncate(output_path, std::ios::trunc); }
   try {
     ms::bio::Manager manager(1u << macro_refinement, 1u << micro_refinement, input_path, output_path, num_threads,

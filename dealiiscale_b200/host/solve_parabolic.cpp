@@ -15,6 +15,7 @@ int main(int argc, char* argv[]) {
   const std::string output_path = "results/" + id + "_convergence_table.txt";
   ms::Distributed& dist = ms::distributed();  // one process per GPU when RANK / WORLD_SIZE / LOCAL_RANK are set
   if (dist.rank != 0 && !std::freopen("/dev/null", "w", stdout)) return 3;
+  ms::ensure_directory("results");  // the reference expects it to exist (populate.sh links it)
   if (dist.rank == 0) { std::ofstream truncate(output_path, std::ios::trunc); }
   try {
     for (int i = 0; i < levels; i++) {
