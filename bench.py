@@ -421,6 +421,9 @@ def main():
             threads = os.cpu_count() or 1
             line["cpu_baseline"] = cpu_baseline(prm_path, macro_cells, micro_cells, args.cpu_sample or 128 * threads,
                                                 threads)
+            # what solve_elliptic / solve_parabolic do in the reference: one thread over the grids
+            one = cpu_baseline(prm_path, macro_cells, micro_cells, 49, 1)
+            line["cpu_baseline"]["single_thread"] = {"value": one["value"], "unit": UNIT, "sample": one["sample"]}
         print(json.dumps(line), flush=True)
     ms.close()
     if distributed:
