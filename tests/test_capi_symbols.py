@@ -59,3 +59,15 @@ def test_product_never_touches_the_oracle():
                 for needle in ("liboracle", "oracle/_build", "oracle/_ref", 'include "../../oracle', "import oracle",
                                "from oracle", "load_oracle", "helpers import"):
                     assert needle not in text, (f, needle)
+
+
+def test_cmake_build_lists_the_same_sources_as_the_in_tree_recipe():
+    """CMakeLists.txt (for a CMake host project) and dealiiscale_b200/build.py (tests, bench) build the same library."""
+    from dealiiscale_b200 import build
+
+    text = open(os.path.join(ROOT, "CMakeLists.txt")).read()
+    for src in build.CUDA_SOURCES + build.HOST_SOURCES:
+        assert "${CSRC}/" + src in text, src
+    for exe in ("solve_elliptic", "solve_biomath", "solve_parabolic"):
+        assert exe in text
+    assert "CMAKE_CUDA_ARCHITECTURES 100a" in text
