@@ -26,6 +26,20 @@ namespace ms {
 class Distributed {
  public:
   int rank = 0, world = 1, local_rank = 0;
+  // Ranks that take part in the CURRENT problem (set by the driver before it builds a Manager).  The partition
+  // gives rank r the block [r B, min((r+1) B, N)) with B = ceil(N / R); with few macro points and many ranks the
+  // last blocks would be empty (N = 9 on 4 ranks: 3 + 3 + 3 + 0), so a coarse level runs on the largest R <= world
+  // that leaves nobody empty and the other ranks sit the level out (MicroSolver::idle_setup keeps them in step
+  // with the out-of-band exchanges).
+  int level_ranks = 0;
+  int ranks_in_use() const { return level_ranks > 0 ? level_ranks : world; }
+  bool sits_out() const { return rank >= ranks_in_use(); }
+  static int usable_ranks(int n_total, int world) {
+    int R = world < 1 ? 1 : world;
+    while (R > 1 && static_cast<long long>(R - 1) * ((n_total + R - 1) / R) >= n_total) --R;
+    return R;
+  }
+  void plan_level(int n_total) { level_ranks = usable_ranks(n_total, world); }
 
   static Distributed from_env() {
     Distributed d;

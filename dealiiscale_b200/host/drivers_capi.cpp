@@ -56,6 +56,9 @@ int msdrv_rendezvous_selftest(int rounds) {
   });
 }
 
+// Distributed::usable_ranks: the largest rank count <= world for which no block of msgpu_partition is empty
+int msdrv_usable_ranks(int n_total, int world) { return ms::Distributed::usable_ranks(n_total, world); }
+
 // ---- solution files (output.h): host-only, no device involved -----------------------------------
 // format 0 = DataOut::write_gnuplot, 1 = DataOut::write_vtk; nodal[(nc+1)^2] in the reference numbering of the mesh kind
 int msdrv_write_solution(const char* path, int format, int mesh_kind, int cells_per_axis, const double* nodal,

@@ -52,29 +52,48 @@ class MicroSolver {
   void set_grid_locations(const std::vector<std::array<double, 2>>& locations) {
     n_total_ = static_cast<int>(locations.size());
     Distributed& d = distributed();
+    if (d.sits_out()) throw std::runtime_error("this rank sits the level out (Distributed::plan_level)");
+    ranks_ = d.active() ? d.ranks_in_use() : 1;
     k0_ = 0;
     k1_ = n_total_;
-    if (d.active()) check(msgpu_partition(n_total_, d.world, d.rank, &k0_, &k1_));
+    if (ranks_ > 1) check(msgpu_partition(n_total_, ranks_, d.rank, &k0_, &k1_));
     num_grids_ = k1_ - k0_;
+    if (num_grids_ < 1) throw std::runtime_error("empty block of macro points: call Distributed::plan_level first");
     check(msgpu_set_grid_locations(ctx_, &locations[k0_][0], num_grids_));
+  }
+  // Whether the fused coupling + allgather over peer memory is used (up to 8 ranks; MSGPU_NCCL_ALLGATHER=1: NCCL).
+  static bool wants_p2p(int ranks) {
+    const char* nccl_only = std::getenv("MSGPU_NCCL_ALLGATHER");
+    return ranks > 1 && ranks <= 8 && !(nccl_only && nccl_only[0] == '1');
   }
   void setup() {
     Distributed& d = distributed();
-    if (d.active()) {  // ncclGetUniqueId on rank 0 -> everybody -> ncclCommInitRank
+    if (d.active()) {  // ncclGetUniqueId on rank 0 -> everybody -> ncclCommInitRank over the ranks in use
       char id[128] = {};
-      if (d.rank == 0) check(msgpu_comm_unique_id(id));
+      if (d.rank == 0 && ranks_ > 1) check(msgpu_comm_unique_id(id));
       d.broadcast(id, sizeof id, 0);
-      check(msgpu_comm_init(ctx_, id, d.rank, d.world, n_total_, k0_));
+      if (ranks_ > 1) check(msgpu_comm_init(ctx_, id, d.rank, ranks_, n_total_, k0_));
     }
     check(msgpu_setup(ctx_));
-    const char* nccl_only = std::getenv("MSGPU_NCCL_ALLGATHER");
-    if (d.active() && d.world <= 8 && !(nccl_only && nccl_only[0] == '1')) {
+    if (d.active() && wants_p2p(d.ranks_in_use())) {
       // fused coupling + allgather over peer memory (csrc/comm.cu): exchange the 64-byte IPC handles
-      unsigned char mine[64];
-      check(msgpu_comm_p2p_export(ctx_, mine));
+      unsigned char mine[64] = {};
+      if (ranks_ > 1) check(msgpu_comm_p2p_export(ctx_, mine));
       std::vector<unsigned char> all;
       d.allgather(mine, sizeof mine, all);
-      check(msgpu_comm_p2p_attach(ctx_, all.data()));
+      if (ranks_ > 1) check(msgpu_comm_p2p_attach(ctx_, all.data()));  // the first ranks_ handles
+    }
+  }
+  // A rank that sits a level out performs the same out-of-band exchanges as the ranks that work on it.
+  static void idle_setup() {
+    Distributed& d = distributed();
+    if (!d.active()) return;
+    char id[128] = {};
+    d.broadcast(id, sizeof id, 0);
+    if (wants_p2p(d.ranks_in_use())) {
+      unsigned char mine[64] = {};
+      std::vector<unsigned char> all;
+      d.allgather(mine, sizeof mine, all);
     }
   }
   int first_grid() const { return k0_; }           // global index of this rank's first micro system
@@ -179,7 +198,7 @@ class MicroSolver {
   // ncclBroadcast (BASELINE.json north_star; msgpu_broadcast_macro also places this rank's block on the device).
   static bool macro_broadcast() {
     const char* e = std::getenv("MSGPU_MACRO_BROADCAST");
-    return distributed().active() && e && e[0] == '1';
+    return distributed().active() && distributed().ranks_in_use() > 1 && e && e[0] == '1';
   }
   static bool solves_macro_here() { return !macro_broadcast() || distributed().rank == 0; }
   void share_macro_solution(std::vector<double>& u, std::vector<double>* w = nullptr) {
@@ -193,6 +212,7 @@ class MicroSolver {
   msgpu_ctx* ctx_ = nullptr;
   int problem_, cells_, n_dofs_ = 0, num_grids_ = 0, macro_fields_ = 0;
   int n_total_ = 0, k0_ = 0, k1_ = 0;  // all grids / this rank's block
+  int ranks_ = 1;                      // ranks sharing this problem
   const std::vector<double>*macro_u_ = nullptr, *macro_w_ = nullptr;
   void push_macro() {
     if (!macro_u_) throw std::runtime_error("set_macro_solution was not called");

@@ -24,6 +24,13 @@ int main(int argc, char* argv[]) {
   ms::ensure_directory("results");  // the reference expects it to exist (populate.sh links it)
   if (dist.rank == 0) { std::ofstream truncate(output_path, std::ios::trunc); }
   try {
+    const int macro_nodes = (1 << macro_refinement) + 1;
+    dist.plan_level(macro_nodes * macro_nodes);  // a coarse macro mesh may have fewer points than the job has ranks
+    if (dist.sits_out()) {
+      ms::MicroSolver::idle_setup();
+      dist.finalize();
+      return 0;
+    }
     ms::bio::Manager manager(1u << macro_refinement, 1u << micro_refinement, input_path, output_path, num_threads,
                              dist.active() ? dist.local_rank : -1);
     if (const char* e = std::getenv("MSGPU_CYCLE_LIMIT")) manager.cycle_limit = std::atoi(e);  // extension: stop after K cycles

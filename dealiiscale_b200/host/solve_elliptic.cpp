@@ -22,6 +22,12 @@ int main(int argc, char* argv[]) {
   if (dist.rank == 0) { std::ofstream truncate(output_path, std::ios::trunc); }
   try {
     for (unsigned int i = 2; i < 6; i++) {
+      const int macro_nodes = (1 << (i - 1)) + 1;
+      dist.plan_level(macro_nodes * macro_nodes);  // coarse levels have fewer macro points than a big job has ranks
+      if (dist.sits_out()) {
+        ms::MicroSolver::idle_setup();
+        continue;
+      }
       ms::elliptic::Manager manager(i - 1, i, input_path, output_path, dist.active() ? dist.local_rank : -1);
       if (const char* e = std::getenv("MSGPU_CYCLE_LIMIT")) manager.cycle_limit = std::atoi(e);  // extension: stop after K cycles
       manager.setup();

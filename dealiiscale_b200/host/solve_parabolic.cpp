@@ -21,6 +21,11 @@ int main(int argc, char* argv[]) {
     for (int i = 0; i < levels; i++) {
       const auto h_inv = static_cast<unsigned int>(std::round(8 * std::pow(2, i / 2.)));
       const auto t_inv = static_cast<unsigned int>(std::round(4 * std::pow(2, i)));
+      dist.plan_level(static_cast<int>((h_inv + 1) * (h_inv + 1)));
+      if (dist.sits_out()) {
+        ms::MicroSolver::idle_setup();
+        continue;
+      }
       ms::parabolic::TimeManager manager(h_inv, h_inv, t_inv, input_path, output_path,
                                          dist.active() ? dist.local_rank : -1);
       manager.setup();

@@ -91,3 +91,20 @@ def test_cpp_driver_rendezvous_between_processes(tmp_path):
                                        MSGPU_RENDEZVOUS_DIR=rdzv)) for r in range(3)]
     assert [p.wait(timeout=120) for p in procs] == [0, 0, 0]
     assert not os.path.exists(rdzv)  # rank 0 removed the exchange directory after the last barrier
+
+
+def test_coarse_levels_use_only_as_many_ranks_as_have_macro_points():
+    """host/distributed.h: with B = ceil(N / R) the last blocks of the partition can be empty (N = 9 on 4 ranks);
+    the drivers then run the level on the largest R that leaves no rank empty and the others sit it out."""
+    import ctypes
+
+    lib = ctypes.CDLL(os.path.join(ROOT, "dealiiscale_b200", "_build", "libmsdrivers.so"))
+    cases = ((9, 4), (9, 8), (25, 8), (4225, 8), (1, 8), (9, 2), (81, 8))
+    assert [lib.msdrv_usable_ranks(n, w) for n, w in cases] == [3, 5, 7, 8, 1, 2, 8]
+    for n in range(1, 200):
+        for w in range(1, 9):
+            r = lib.msdrv_usable_ranks(n, w)
+            blocks = [partition(n, r, k) for k in range(r)]
+            assert 1 <= r <= w and all(k1 > k0 for k0, k1 in blocks) and blocks[-1][1] == n
+            if r < w:  # one more rank would leave somebody without work
+                assert any(k1 <= k0 for k0, k1 in (partition(n, r + 1, k) for k in range(r + 1)))

@@ -36,24 +36,31 @@ def _run(tmp, name, exe_args, ranks, port, env_extra=None):
     return work, r.stdout
 
 
+RANKS = int(os.environ.get("MSGPU_TEST_RANKS", "2"))  # 4: coarse levels leave ranks without macro points (they sit out)
+QUICK = os.environ.get("MSGPU_TEST_QUICK") == "1"       # fused exchange and broadcast variants only
+
 CASES = [
     ("bio", ["solve_biomath", "input/linear.prm", "3", "4", "0"], "out.txt"),
     ("bio_nosol", ["solve_biomath", "input/biocase.prm", "2", "3", "0"], None),  # residual-based stop, MSGPU_CYCLE_LIMIT
     ("ell", ["solve_elliptic", "input/elliptic_non_linear.prm"], "elliptic_non_linear_convergence_table.txt"),
     ("par", ["solve_parabolic", "input/linear_time.prm", "2"], "linear_time_convergence_table.txt"),
+    ("bio_tiny", ["solve_biomath", "input/linear.prm", "1", "3", "0"], "out.txt"),  # 9 macro points
 ]
 
 
 @pytest.mark.parametrize("name,args,table", CASES)
-def test_two_ranks_reproduce_the_single_process_run(tmp_path, name, args, table):
-    if _n_gpus() < 2:
-        pytest.skip("needs two GPUs")
+def test_several_ranks_reproduce_the_single_process_run(tmp_path, name, args, table):
+    if _n_gpus() < RANKS:
+        pytest.skip(f"needs {RANKS} GPUs")
     base = {"MSGPU_CYCLE_LIMIT": "4"} if name == "bio_nosol" else {}
     one, out1 = _run(str(tmp_path), name + "_1", args, 1, 0, base)
-    for tag, env in (("p2p", {}), ("nccl", {"MSGPU_NCCL_ALLGATHER": "1"}), ("hostmacro", {"MSGPU_HOST_MACRO": "1"}),
-                     ("bcast", {"MSGPU_MACRO_BROADCAST": "1"}),  # rank 0 solves the macro system, ncclBroadcast
-                     ("bcasthost", {"MSGPU_MACRO_BROADCAST": "1", "MSGPU_HOST_MACRO": "1"})):
-        two, out2 = _run(str(tmp_path), f"{name}_2_{tag}", args, 2, 29700 + len(tag), dict(base, **env))
+    variants = [("p2p", {}), ("nccl", {"MSGPU_NCCL_ALLGATHER": "1"}), ("hostmacro", {"MSGPU_HOST_MACRO": "1"}),
+                ("bcast", {"MSGPU_MACRO_BROADCAST": "1"}),  # rank 0 solves the macro system, ncclBroadcast
+                ("bcasthost", {"MSGPU_MACRO_BROADCAST": "1", "MSGPU_HOST_MACRO": "1"})]
+    if QUICK:
+        variants = [variants[0], variants[3]]
+    for tag, env in variants:
+        two, out2 = _run(str(tmp_path), f"{name}_{RANKS}_{tag}", args, RANKS, 29700 + len(tag), dict(base, **env))
         if table:
             t1 = open(os.path.join(one, "results", table)).read()
             t2 = open(os.path.join(two, "results", table)).read()
