@@ -262,37 +262,64 @@ def _emul_with_rhs(expr, consts):
     return e, xy
 
 
+def _generated_code_equals_interpreter(tmp_path, n, expr, consts):
+    e, xy = _emul_with_rhs(expr, consts)
+    src = _source(e)
+    cpp = tmp_path / f"k{n}.cpp"
+    cpp.write_text(SHIM + src + DRIVER)
+    so = tmp_path / f"k{n}.so"
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                           "-Wno-unknown-pragmas", "-o", str(so), str(cpp)])
+    lib = C.CDLL(str(so))
+    N, ncells = len(xy), 4
+    e.assemble(np.ones(N), np.ones(N))
+    want = np.zeros(N * 18 * ncells)
+    e.lib.emul_get_cell_scratch.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+    e.lib.emul_get_cell_scratch(e.h, dptr(want), want.size)
+    slots, t0, t1 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    dims = (C.c_int * 10)()
+    e.lib.emul_table_pointers.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 3 + [C.POINTER(C.c_int)]
+    e.lib.emul_table_pointers(e.h, C.byref(slots), C.byref(t0), C.byref(t1), dims)
+    e.lib.emul_mesh_h.restype = C.c_double
+    e.lib.emul_mesh_h.argtypes = [C.c_void_p]
+    got = np.zeros_like(want)
+    flag = C.c_int(0)
+    lib.host_run.argtypes = [C.POINTER(C.c_int), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                             C.c_double, C.c_void_p, C.POINTER(C.c_int)]
+    lib.host_run(dims, e.lib.emul_mesh_h(e.h), slots, t0, t1, N, 1.0, dptr(got), C.byref(flag))
+    got, want = got.reshape(N, 18, ncells), want.reshape(N, 18, ncells)
+    assert np.isfinite(want[:, 10:14]).all(), expr
+    assert np.array_equal(got[:, 10:14, :], want[:, 10:14, :]), expr
+    e.close()
+
+
 def test_every_opcode_is_lowered_like_the_interpreter_executes_it(tmp_path):
     """The expression list of test_expr_compile.py (all operators and functions of the grammar) as right-hand
     sides: the generated straight-line code, run on the host, must reproduce the interpreter bit for bit."""
     from test_expr_compile import CONSTS, EXPRS
 
     for n, expr in enumerate(EXPRS):
-        e, xy = _emul_with_rhs(expr, CONSTS)
-        src = _source(e)
-        cpp = tmp_path / f"k{n}.cpp"
-        cpp.write_text(SHIM + src + DRIVER)
-        so = tmp_path / f"k{n}.so"
-        subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
-                               "-Wno-unknown-pragmas", "-o", str(so), str(cpp)])
-        lib = C.CDLL(str(so))
-        N, ncells = len(xy), 4
-        e.assemble(np.ones(N), np.ones(N))
-        want = np.zeros(N * 18 * ncells)
-        e.lib.emul_get_cell_scratch.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
-        e.lib.emul_get_cell_scratch(e.h, dptr(want), want.size)
-        slots, t0, t1 = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        dims = (C.c_int * 10)()
-        e.lib.emul_table_pointers.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 3 + [C.POINTER(C.c_int)]
-        e.lib.emul_table_pointers(e.h, C.byref(slots), C.byref(t0), C.byref(t1), dims)
-        e.lib.emul_mesh_h.restype = C.c_double
-        e.lib.emul_mesh_h.argtypes = [C.c_void_p]
-        got = np.zeros_like(want)
-        flag = C.c_int(0)
-        lib.host_run.argtypes = [C.POINTER(C.c_int), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
-                                 C.c_double, C.c_void_p, C.POINTER(C.c_int)]
-        lib.host_run(dims, e.lib.emul_mesh_h(e.h), slots, t0, t1, N, 1.0, dptr(got), C.byref(flag))
-        got, want = got.reshape(N, 18, ncells), want.reshape(N, 18, ncells)
-        assert np.isfinite(want[:, 10:14]).all(), expr
-        assert np.array_equal(got[:, 10:14, :], want[:, 10:14, :]), expr
-        e.close()
+        _generated_code_equals_interpreter(tmp_path, n, expr, CONSTS)
+
+
+def _random_expression(rng, depth):
+    """A random member of the grammar exercised by tests/test_expr_random.py (all values finite on [-1,1]^4)."""
+    if depth == 0 or rng.random() < 0.15:
+        return rng.choice(["x0", "x1", "y0", "y1", "0.5", "2", "1.25", "7e-1", "D_2", "kappa_1"])
+    a = _random_expression(rng, depth - 1)
+    b = _random_expression(rng, depth - 1)
+    return rng.choice([
+        f"({a} + {b})", f"({a} - {b})", f"{a}*{b}", f"{a}/(2 + sin({b}))", f"-{a}", f"({a})^2", f"({a})^3",
+        f"sin({a})", f"cos ({a})", f"tanh({a})", f"exp(sin({a}))", f"sqrt(abs({a}))", f"log(1 + abs({a}))",
+        f"min({a}, {b})", f"max({a}, {b}, 0.5)", f"if({a} > {b}, {a}, -{b})", f"(({a} < {b}) | ({a} >= 1))",
+        f"pow(1 + abs({a}), sin({b}))", f"atan2({a}, 2 + cos({b}))",
+    ])
+
+
+def test_generated_code_equals_interpreter_on_random_expressions(tmp_path):
+    import random
+
+    rng = random.Random(20261020)
+    consts = {"D_2": 1.25, "kappa_1": 0.7}
+    for n in range(16):
+        _generated_code_equals_interpreter(tmp_path, 100 + n, _random_expression(rng, 4), consts)
