@@ -177,6 +177,32 @@ class RobinSystem:
         self.x = spla.spsolve(self.A.tocsc(), self.b)
         return self.x
 
+    def flux(self, side, kappa=1.0, x=None):
+        """The micro -> macro flux integral of the bio driver over the inflow (side 0, x-min) or outflow (side 1, x-max)
+        boundary: sum over faces and points of (-kappa v_h + bc(zeta)) JxW |F R n|  (src/bio-multiscale/macro.cpp:254-296);
+        bc is this system's left / right Robin function."""
+        x = self.x if x is None else x
+        nc, h = self.nc, self.h
+        sf, wf = gauss01(self.qf)
+        cx = 0 if side == 0 else nc - 1
+        fxi = np.zeros_like(sf) if side == 0 else np.ones_like(sf)
+        nrm = (-1.0, 0.0) if side == 0 else (1.0, 0.0)
+        name = "left_robin" if side == 0 else "right_robin"
+        tot = 0.0
+        for cy in range(nc):
+            x0, y0 = -1.0 + cx * h, -1.0 + cy * h
+            dofs = [self.node(cx, cy), self.node(cx + 1, cy), self.node(cx, cy + 1), self.node(cx + 1, cy + 1)]
+            Xf, Yf = x0 + h * fxi, y0 + h * sf
+            Ff = evaluate(self.p["jac_mapping"], Xf, Yf)
+            rn = (-nrm[1], nrm[0])
+            jb = np.sqrt((Ff[0] * rn[0] + Ff[1] * rn[1]) ** 2 + (Ff[2] * rn[0] + Ff[3] * rn[1]) ** 2)
+            zfx, zfy = evaluate(self.p["mapping"], Xf, Yf)
+            g = evaluate(self.p[name], zfx, zfy)[0]
+            vf, _, _ = _shape(fxi, sf)
+            vh = sum(x[dofs[i]] * vf[i] for i in range(4))
+            tot += np.sum((-kappa * vh + g) * wf * h * jb)
+        return float(tot)
+
     def l2_error(self, x=None, q=5):
         """integrate_difference against ref_solution with QGauss(5), L2 norm (transform.cpp:377-386)."""
         x = self.x if x is None else x

@@ -88,6 +88,13 @@ def test_kernel_bodies_assemble_the_transform_system(prm):
     assert rc == 0
     x = s.solve()[perm]
     assert rel_l2(e.solution(0), x) < 1e-8  # CG at 1e-10 absolute against the direct solve
+    # the flux integrals the bio macro solver takes from this system (bio macro.cpp:254-296), with the same solution
+    xo = np.zeros_like(x)
+    xo[perm] = e.solution(0)
+    cu, cw = e.coupling()
+    for got, side in ((cu[0], 0), (cw[0], 1)):
+        want = s.flux(side, 1.0, xo)
+        assert abs(got - want) <= 1e-11 * max(1.0, abs(want))
     e.close()
 
 
