@@ -63,6 +63,8 @@ def test_cpp_oracle_and_kernel_bodies_match_the_checker(prm):
     e.solve(1e-12, 1000)
     perm = _perm(8)
     bulk_e, _ = e.coupling()
+    l2_e, _ = e.errors()          # per-grid L2 error against micro_solution (micro.cpp:193-202)
+    l2_o, _ = o.grid_errors()
     for k in (0, 4, 7):
         s = dirichlet_single.DirichletSystem(_strings(data), tuple(xy[k]), u[k], 8).assemble()
         x = s.solve()[perm]
@@ -75,6 +77,7 @@ def test_cpp_oracle_and_kernel_bodies_match_the_checker(prm):
         assert rel_l2(e.rhs(k), s.b[perm]) < 1e-12
         assert rel_l2(e.solution(k), x) < 1e-10
         assert abs(bulk_e[k] - s.bulk()) <= 1e-10 * max(1.0, abs(s.bulk()))
+        assert abs(l2_e[k] - s.l2_error()) <= 1e-9 and abs(l2_o[k] - s.l2_error()) <= 1e-9
     e.close()
     o.close()
 
