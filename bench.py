@@ -284,10 +284,33 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         ms.attach_communicator(ids[0], rank, n_gpus, n_total)
     ms.setup()
-    if distributed and not args.nccl_allgather:
+    fused_exchange = distributed and not args.nccl_allgather
+    if fused_exchange:
+        # peer-memory exchange; if CUDA IPC is refused on any rank, every rank goes back to ncclAllGather together
+        ok = 1
+        try:
+            if os.environ.get("MSGPU_BENCH_FAIL_P2P") == str(rank):  # test hook: this rank pretends CUDA IPC is refused
+                raise capi.MsgpuError(capi.ERR_CUDA, "simulated")
+            mine = ms.p2p_export()
+        except capi.MsgpuError as err:
+            mine, ok = b"\0" * 64, 0
+            print(f"[bench] rank {rank}: p2p export failed ({err}); falling back to ncclAllGather", file=sys.stderr)
         handles = [None] * n_gpus
-        dist.all_gather_object(handles, ms.p2p_export())
-        ms.p2p_attach(handles)
+        dist.all_gather_object(handles, mine)
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            try:
+                ms.p2p_attach(handles)
+            except capi.MsgpuError as err:
+                ok = 0
+                print(f"[bench] rank {rank}: p2p attach failed ({err}); falling back to ncclAllGather", file=sys.stderr)
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            ms.p2p_detach()
+            fused_exchange = False
+            args.nccl_allgather = True
     n = ms.n_dofs
     m = micro_cells + 1
     nnz = (3 * m - 2) ** 2

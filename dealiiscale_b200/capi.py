@@ -27,7 +27,7 @@ EXPORTED = [
     "msgpu_comm_unique_id", "msgpu_partition", "msgpu_comm_init", "msgpu_broadcast_macro", "msgpu_enable_timing",
     "msgpu_get_stats", "msgpu_jit_log", "msgpu_macro_setup", "msgpu_macro_set_system", "msgpu_macro_set_rhs",
     "msgpu_macro_set_solution", "msgpu_macro_get_solution", "msgpu_macro_solve", "msgpu_comm_p2p_export",
-    "msgpu_comm_p2p_attach", "msgpu_set_exact_solution", "msgpu_comm_allgather",
+    "msgpu_comm_p2p_attach", "msgpu_set_exact_solution", "msgpu_comm_allgather", "msgpu_comm_p2p_detach",
 ]
 
 
@@ -89,6 +89,7 @@ def load():
     lib.msgpu_residuals.argtypes = [vp, dp]
     lib.msgpu_set_exact_solution.argtypes = [vp, C.c_double]
     lib.msgpu_comm_allgather.argtypes = [vp, dp, dp, C.c_int]
+    lib.msgpu_comm_p2p_detach.argtypes = [vp]
     lib.msgpu_get_solutions.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.msgpu_set_solutions.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.msgpu_zero_solutions.argtypes = [vp]

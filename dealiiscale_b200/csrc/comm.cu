@@ -322,6 +322,21 @@ int msgpu_comm_allgather(msgpu_ctx* ctx, const double* local, double* all, int f
   return MSGPU_OK;
 }
 
+// Leaves the peer-memory exchange again (msgpu_coupling goes back to ncclAllGather).  Safe to call when nothing is
+// attached: hosts use it to fall back consistently when msgpu_comm_p2p_attach failed on any rank.
+int msgpu_comm_p2p_detach(msgpu_ctx* ctx) {
+  if (!ctx) return MSGPU_ERR_INVALID;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return MSGPU_ERR_CUDA;
+  cudaStreamSynchronize(ctx->stream);
+  for (int p = 0; p < ctx->n_ranks && p < 8; ++p) {
+    if (p != ctx->rank && ctx->p2p_peer[p]) cudaIpcCloseMemHandle(ctx->p2p_peer[p]);
+    ctx->p2p_peer[p] = nullptr;
+  }
+  cudaGetLastError();
+  ctx->p2p_ready = 0;
+  return MSGPU_OK;
+}
+
 // u_all / w_all: [n_total] host arrays; significant on root, overwritten on the other ranks.
 int msgpu_broadcast_macro(msgpu_ctx* ctx, double* u_all, double* w_all, int root) {
   if (!ctx || !ctx->comm_ready || !ctx->setup_done || !u_all) return MSGPU_ERR_INVALID;

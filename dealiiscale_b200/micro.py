@@ -270,6 +270,10 @@ class MicroSolver:
         self._check(self.lib.msgpu_comm_allgather(self.h, _d(loc), _d(out), fields))
         return out[0] if fields == 1 else tuple(out)
 
+    def p2p_detach(self):
+        """Back to the NCCL allgather (e.g. after ``p2p_attach`` failed on some rank)."""
+        self._check(self.lib.msgpu_comm_p2p_detach(self.h))
+
     def broadcast_macro(self, u_all, w_all=None, root=0):
         u_all = np.ascontiguousarray(u_all, dtype=np.float64)
         wp = None

@@ -178,6 +178,8 @@ int msgpu_comm_init(msgpu_ctx* ctx, const char id[128], int rank, int n_ranks, i
  * with a flag per peer and awaited with a stream memory operation; the NCCL allgather is gone. <= 8 ranks. */
 int msgpu_comm_p2p_export(msgpu_ctx* ctx, unsigned char handle[64]);
 int msgpu_comm_p2p_attach(msgpu_ctx* ctx, const unsigned char* handles /* [n_ranks][64] */);
+/* Back to the NCCL allgather (also after a failed attach on this or another rank); a no-op when nothing is attached. */
+int msgpu_comm_p2p_detach(msgpu_ctx* ctx);
 /* Per-grid scalars of all ranks, e.g. the error / residual norms the stop test aggregates over the macro mesh
  * (micro.cpp:206-214): local[fields][msgpu_num_grids] -> all[fields][n_total] on every rank, fields <= 2.
  * One grouped ncclAllGather (needs the communicator); without msgpu_comm_init it is a plain copy. */
