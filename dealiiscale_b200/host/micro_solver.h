@@ -9,6 +9,7 @@
 // library cannot create a context the constructor throws.
 #pragma once
 #include <array>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -76,12 +77,30 @@ class MicroSolver {
     }
     check(msgpu_setup(ctx_));
     if (d.active() && wants_p2p(d.ranks_in_use())) {
-      // fused coupling + allgather over peer memory (csrc/comm.cu): exchange the 64-byte IPC handles
-      unsigned char mine[64] = {};
-      if (ranks_ > 1) check(msgpu_comm_p2p_export(ctx_, mine));
+      // fused coupling + allgather over peer memory (csrc/comm.cu): exchange the 64-byte IPC handles.  If CUDA IPC is
+      // refused anywhere (export or attach), every rank drops back to the NCCL allgather together.
+      unsigned char mine[65] = {};  // [0]: this rank could export, [1..64]: its handle
+      const char* fail = std::getenv("MSGPU_TEST_FAIL_P2P");  // test hook: that rank pretends CUDA IPC is refused
+      const bool pretend = fail && std::atoi(fail) == d.rank;
+      if (ranks_ > 1 && !pretend) mine[0] = msgpu_comm_p2p_export(ctx_, mine + 1) == MSGPU_OK ? 1 : 0;
       std::vector<unsigned char> all;
       d.allgather(mine, sizeof mine, all);
-      if (ranks_ > 1) check(msgpu_comm_p2p_attach(ctx_, all.data()));  // the first ranks_ handles
+      bool everybody = true;
+      std::vector<unsigned char> handles(static_cast<size_t>(ranks_) * 64);
+      for (int r = 0; r < ranks_; ++r) {
+        everybody = everybody && all[static_cast<size_t>(r) * 65] == 1;
+        std::copy(all.begin() + static_cast<size_t>(r) * 65 + 1, all.begin() + static_cast<size_t>(r + 1) * 65,
+                  handles.begin() + static_cast<size_t>(r) * 64);
+      }
+      unsigned char attached = 0;
+      if (ranks_ > 1 && everybody) attached = msgpu_comm_p2p_attach(ctx_, handles.data()) == MSGPU_OK ? 1 : 0;
+      d.allgather(&attached, 1, all);
+      bool all_attached = everybody;
+      for (int r = 0; r < ranks_; ++r) all_attached = all_attached && all[r] == 1;
+      if (ranks_ > 1 && !all_attached) {
+        check(msgpu_comm_p2p_detach(ctx_));
+        if (d.rank == 0) std::fprintf(stderr, "msgpu: peer-memory exchange unavailable, using ncclAllGather\n");
+      }
     }
   }
   // A rank that sits a level out performs the same out-of-band exchanges as the ranks that work on it.
@@ -91,9 +110,10 @@ class MicroSolver {
     char id[128] = {};
     d.broadcast(id, sizeof id, 0);
     if (wants_p2p(d.ranks_in_use())) {
-      unsigned char mine[64] = {};
+      unsigned char mine[65] = {}, attached = 0;
       std::vector<unsigned char> all;
       d.allgather(mine, sizeof mine, all);
+      d.allgather(&attached, 1, all);
     }
   }
   int first_grid() const { return k0_; }           // global index of this rank's first micro system

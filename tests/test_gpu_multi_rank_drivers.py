@@ -56,9 +56,10 @@ def test_several_ranks_reproduce_the_single_process_run(tmp_path, name, args, ta
     one, out1 = _run(str(tmp_path), name + "_1", args, 1, 0, base)
     variants = [("p2p", {}), ("nccl", {"MSGPU_NCCL_ALLGATHER": "1"}), ("hostmacro", {"MSGPU_HOST_MACRO": "1"}),
                 ("bcast", {"MSGPU_MACRO_BROADCAST": "1"}),  # rank 0 solves the macro system, ncclBroadcast
-                ("bcasthost", {"MSGPU_MACRO_BROADCAST": "1", "MSGPU_HOST_MACRO": "1"})]
+                ("bcasthost", {"MSGPU_MACRO_BROADCAST": "1", "MSGPU_HOST_MACRO": "1"}),
+                ("p2pfail", {"MSGPU_TEST_FAIL_P2P": "1"})]  # rank 1 cannot export: everybody falls back to NCCL
     if QUICK:
-        variants = [variants[0], variants[3]]
+        variants = [variants[0], variants[3], variants[5]]
     for tag, env in variants:
         two, out2 = _run(str(tmp_path), f"{name}_{RANKS}_{tag}", args, RANKS, 29700 + len(tag), dict(base, **env))
         if table:
