@@ -55,3 +55,31 @@ def test_malformed_lines(tmp_path):
     ph.declare_entry("a", "1")
     with pytest.raises(PrmError):
         ph.parse_input(str(tmp_path / "missing.prm"))
+
+
+def test_every_committed_parameter_file_belongs_to_exactly_one_driver():
+    """ParameterHandler aborts on undeclared keys (pde_data.cpp:8-23, :40-65, :110-126), so each .prm works with its own
+    driver only: *map_test / elliptic_* -> solve_elliptic, linear / biocase* -> solve_biomath, *time* /
+    full_nonlinear / ... -> solve_parabolic; parsed_mapping and ss_* belong to playground/transform.cpp."""
+    import os
+
+    from helpers import INPUT
+    from dealiiscale_b200.prm import BioData, EllipticData, TwoPressureData
+
+    owners = {}
+    for f in sorted(os.listdir(INPUT)):
+        if not f.endswith(".prm"):
+            continue
+        ok = []
+        for cls in (EllipticData, BioData, TwoPressureData):
+            try:
+                cls(os.path.join(INPUT, f))
+                ok.append(cls.__name__)
+            except Exception:  # noqa: BLE001 (ParameterHandler errors of any kind)
+                pass
+        owners[f] = ok
+    assert all(len(v) <= 1 for v in owners.values()), owners
+    assert {f for f, v in owners.items() if not v} == {"parsed_mapping.prm", "ss_lin_equiv.prm", "ss_smt_equivalent.prm"}
+    assert owners["map_test.prm"] == ["EllipticData"] and owners["biocase.prm"] == ["BioData"]
+    assert owners["linear.prm"] == ["BioData"]  # BASELINE.json configs[0] pairs it with solve_elliptic: see SURVEY.md 8d
+    assert owners["linear_time.prm"] == owners["full_nonlinear.prm"] == ["TwoPressureData"]
