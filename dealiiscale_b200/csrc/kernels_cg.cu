@@ -1339,8 +1339,22 @@ int launch_strip_tmem(cudaStream_t s, const CgArgs& a, int num_sms) {
   // CTAs per SM: bounded by the TMEM columns a CTA allocates (not known to the occupancy calculator), by shared
   // memory and by registers
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem);
   const int by_tmem = 512 / tmem_alloc_columns(BT, K);
+  // ask for the largest shared-memory carve-out: with the default preference the calculator (and the launch) may
+  // settle for a split that holds a single CTA of this size
+  if (by_tmem > 1) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  const cudaError_t occ = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem);
+  if (std::getenv("MSGPU_DEBUG_LAUNCH"))
+    std::fprintf(stderr, "[msgpu] k_cg_strip_tmem<%d,%d>: occupancy query %s -> %d CTAs per SM, TMEM allows %d, smem %zu B\n", BT, K,
+                 cudaGetErrorName(occ), per_sm, by_tmem, smem);
+  // The calculator answers 1 for the 256 x 9 shape although two CTAs fit (2 x 84.5 KB of shared memory, 2 x 32 K
+  // registers — ncu reports both limits as 2).  The kernel is persistent with an atomic work queue, so offering the
+  // hardware by_tmem CTAs per SM is safe either way: a CTA that only becomes resident late finds the queue drained.
+  cudaFuncAttributes fa{};
+  if (by_tmem > per_sm && cudaFuncGetAttributes(&fa, kern) == cudaSuccess &&
+      static_cast<size_t>(by_tmem) * (smem + fa.sharedSizeBytes + 1024) <= 227u * 1024u &&
+      static_cast<long long>(by_tmem) * BT * fa.numRegs <= 65536)
+    per_sm = by_tmem;
   if (per_sm > by_tmem) per_sm = by_tmem;
   if (per_sm < 1) per_sm = 1;
   long long grid = static_cast<long long>(num_sms) * per_sm;
