@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(BUILD, "libmsgpu.so")
 
-CUDA_SOURCES = ["msgpu.cu", "kernels_assemble.cu", "kernels_cg.cu", "kernels_extra.cu", "comm.cu", "macro.cu"]
+CUDA_SOURCES = ["msgpu.cu", "kernels_assemble.cu", "kernels_cg.cu", "kernels_cg_stencil.cu", "kernels_extra.cu", "comm.cu", "macro.cu"]
 HOST_SOURCES = ["expr_compile.cpp", "problem_programs.cpp", "jit.cpp", "jit_codegen.cpp"]
 
 NVCC_FLAGS = [
@@ -44,18 +44,39 @@ def _sources():
     return files, deps
 
 
+def _compile_one(args):
+    src, obj, verbose = args
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    return src, res.returncode, res.stdout + res.stderr
+
+
 def build_msgpu(force: bool = False, verbose: bool = False) -> str:
-    """Compile libmsgpu.so for sm_100a (cross-compiles without a GPU)."""
+    """Compile libmsgpu.so for sm_100a (cross-compiles without a GPU).  One object per source, compiled in
+    parallel and only when the source (or any header) is newer than its object."""
+    from concurrent.futures import ThreadPoolExecutor
+
     files, deps = _sources()
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest(files + deps):
         return LIB
-    os.makedirs(BUILD, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + files + ["-ldl"]
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    objdir = os.path.join(BUILD, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    newest_dep = _newest(deps)
+    jobs, objs = [], []
+    for src in files:
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        objs.append(obj)
+        if force or verbose or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_dep):
+            jobs.append((src, obj, verbose))
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as pool:
+        for src, rc, out in pool.map(_compile_one, jobs):
+            if rc != 0:
+                raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+            if verbose:
+                print(out)
+    res = subprocess.run([_nvcc(), "-shared", "-o", LIB] + objs + ["-ldl"], cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

@@ -16,7 +16,7 @@
 namespace msgpu {
 
 enum Phase { PH_TABLES = 0, PH_MOMENTS, PH_GATHER, PH_CG, PH_COUPLING, PH_COUNT };
-enum FlagSlot { FLAG_JACOBIAN = 0, FLAG_COUNTER = 1, FLAG_CGFAIL = 2 };
+enum FlagSlot { FLAG_JACOBIAN = 0, FLAG_COUNTER = 1, FLAG_CGFAIL = 2, FLAG_STENCIL_BAD = 3 };
 
 // Device-resident macro system(s), see macro.cu.
 struct MacroDevice {
@@ -80,6 +80,8 @@ struct msgpu_ctx {
   int eq_degree = 0;
   double parabolic_dt = -1.0;
   int *d_iters = nullptr, *d_flags = nullptr;
+  double* d_stencil = nullptr;  // [N or 1][STENCIL_TABLE] class tables of class-uniform systems (kernels_cg_stencil.cu)
+  int stencil_hint = 0;         // 0 not known yet, 1 verified for the current matrix, 2 known not class-uniform
   size_t bytes_allocated = 0;
 
   // state

@@ -122,9 +122,32 @@ struct CgArgs {
   double* res;              // [N]
   int* work_counter;        // device int, zeroed by the launcher
   int* fail_flag;           // device int: set to 1 if a system did not converge
+  // Device-side dispatch between two CG kernels launched back to back: with `gate` set, a kernel returns at
+  // once unless (*gate == 0) == (gate_run_if_zero != 0).  No host round trip decides which one does the work.
+  const int* gate = nullptr;
+  int gate_run_if_zero = 0;
+  // Class-compressed matrices (kernels_cg_stencil.cu).  A system whose coefficients do not vary over the mesh
+  // (F constant per system: every bio set, the linear elliptic maps, the parabolic driver) has only nine
+  // distinct matrix rows - one per position class {first, inner, last}^2 - so the CG kernel keeps the stencil
+  // in registers instead of the matrix in tensor memory, and two systems share an SM.
+  double* stencil_ws = nullptr;  // [N or 1][STENCIL_TABLE] class tables, written by the compression kernel; null: off
+  int* stencil_bad = nullptr;    // device int, raised when some system is NOT class-uniform
+  int stencil_hint = 0;          // 0 unknown: compress + verify, both kernels launched behind the gate;
+                                 // 1 verified before (matrix unchanged since): compress only; 2 known not uniform
+  int dirichlet = 0;             // 1: boundary rows are eliminated Dirichlet rows (identity rows, zero couplings):
+                                 //    the CG runs on the inner (m-2)^2 block, the boundary values stay as they are
 };
-// returns launches; *variant = 0 shared-memory resident, 1 global-memory
+constexpr int STENCIL_TABLE = 81;  // 9 position classes x 9 couplings
+// returns launches; *variant = 0 shared-memory resident, 1 global-memory, 2 strip, 3 tensor memory, 4 cluster,
+// 5 class-compressed stencil (decided on the device when stencil_hint == 0)
 int launch_cg(cudaStream_t s, const CgArgs& a, int num_sms, int* variant);
+
+// Class-compressed CG (kernels_cg_stencil.cu).  stencil_supported: is there a strip shape for this mesh;
+// launch_stencil_compress: class tables (+ verification of every stored entry against them);
+// launch_cg_stencil: the solve.  Both return the number of kernels launched, < 0 on error.
+bool stencil_supported(const MeshDims& md, int dirichlet);
+int launch_stencil_compress(cudaStream_t s, const CgArgs& a, int verify);
+int launch_cg_stencil(cudaStream_t s, const CgArgs& a, int num_sms);
 
 // K5/K6 coupling integrals --------------------------------------------------------------------
 struct CouplingArgs {

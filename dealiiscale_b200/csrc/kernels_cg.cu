@@ -26,20 +26,16 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "cg_common.cuh"
 #include "kernels.h"
 
-#ifndef MSGPU_FAST_SCALARS
-#define MSGPU_FAST_SCALARS 1
-#endif
 namespace msgpu {
 
 namespace {
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+using cgc::l2_prefetch_bulk;
+using cgc::strip_dot;
+using cgc::warp_sum;
 
 // Sum over the CTA, result in every thread.  One barrier; `red` must not be reused before the
 // next barrier that follows this call (callers alternate between buffers).
@@ -85,26 +81,11 @@ __device__ __forceinline__ double block_sum_tree(double v, double* red) {
   return t[0];
 }
 
-// Dot-product partial of a strip: NACC independent accumulators (fixed assignment j % NACC, fixed
-// combination order) so that a long strip is not one serial chain of K dependent DFMAs.
-template <int K, int NACC, class F>
-__device__ __forceinline__ double strip_dot(F&& term) {
-  double acc[NACC];
-#pragma unroll
-  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
-#pragma unroll
-  for (int j = 0; j < K; ++j) acc[j % NACC] += term(j);
-#pragma unroll
-  for (int w2 = 1; w2 < NACC; w2 *= 2)
-#pragma unroll
-    for (int i = 0; i + w2 < NACC; i += 2 * w2) acc[i] += acc[i + w2];
-  return acc[0];
-}
-
 // -------------------------------------------------------------------------------------------
 // Shared-memory resident CG.  BT threads, RPT rows per thread (BT*RPT >= n).
 template <int BT, int RPT, bool JACOBI>
 __global__ void __launch_bounds__(BT, 1) k_cg_resident(CgArgs a) {
+  if (a.gate != nullptr && ((*a.gate == 0) != (a.gate_run_if_zero != 0))) return;  // the other CG kernel does the work
   extern __shared__ __align__(16) double sm[];
   __shared__ int s_k;
   const int n = a.md.n, m = a.md.m, ld = a.md.ld;
@@ -283,6 +264,7 @@ __global__ void __launch_bounds__(BT, 1) k_cg_resident(CgArgs a) {
 // Vertical neighbours of a node of colour c have colour c^2, horizontal ones c^1, diagonal ones c^3.
 template <int BT, int K, int PRE>
 __global__ void __launch_bounds__(BT, 1) k_cg_strip(CgArgs a) {
+  if (a.gate != nullptr && ((*a.gate == 0) != (a.gate_run_if_zero != 0))) return;  // the other CG kernel does the work
   constexpr bool JACOBI = PRE == 1;
   constexpr bool SSOR = PRE == 2;
   static_assert(K % 2 == 1, "odd strip length keeps the shared-memory accesses conflict free");
@@ -604,12 +586,6 @@ __device__ __forceinline__ double tmem_get(const TmemRow& q, int i) { return __h
 
 __host__ __device__ constexpr int tmem_pad(int m, int K) { return (m + 3 + K) & ~1; }
 
-// Bulk prefetch of `bytes` (a multiple of 16) starting at the 16-byte block that contains p into L2.
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
-  const unsigned long long addr = reinterpret_cast<unsigned long long>(p) & ~15ull;
-  if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(addr), "r"(bytes) : "memory");
-}
-
 // TMEM columns a CTA of BT threads with K rows per thread allocates: the smallest power of two (>= 32) that holds
 // 14 K + 2 columns for each of the BT/128 warps of a lane quadrant.  Shapes that need less than all 512 columns
 // leave room for further CTAs on the same SM — several small systems in flight per SM, each hiding the
@@ -622,6 +598,7 @@ __host__ __device__ constexpr int tmem_alloc_columns(int BT, int K) {
 
 template <int BT, int K, bool JACOBI>
 __global__ void __launch_bounds__(BT, 512 / tmem_alloc_columns(BT, K)) k_cg_strip_tmem(CgArgs a) {
+  if (a.gate != nullptr && ((*a.gate == 0) != (a.gate_run_if_zero != 0))) return;  // the other CG kernel does the work
   constexpr int ALLOC = tmem_alloc_columns(BT, K);
   constexpr int CW = (ALLOC / (BT / 128)) & ~1;  // TMEM columns per warp
   constexpr int NACC = K >= 12 ? 4 : 1;          // K = 9 stays bit-identical to k_cg_strip
@@ -917,6 +894,7 @@ namespace cg = cooperative_groups;
 
 template <int K, bool JACOBI>
 __global__ void __launch_bounds__(256, 1) k_cg_cluster(CgArgs a) {
+  if (a.gate != nullptr && ((*a.gate == 0) != (a.gate_run_if_zero != 0))) return;  // the other CG kernel does the work
   constexpr int BT = 256, CW = 256, NACC = 4, RC = BT * K;
   static_assert(14 * K + 2 <= CW, "strip must fit the TMEM columns of a thread");
   cg::cluster_group cluster = cg::this_cluster();
@@ -1137,6 +1115,7 @@ __global__ void __launch_bounds__(256, 1) k_cg_cluster(CgArgs a) {
 // recurrence, same reduction order; kept simple — the cluster/DSMEM variant is the next step.
 template <int BT>
 __global__ void __launch_bounds__(BT) k_cg_global(CgArgs a, double* __restrict__ workspace) {
+  if (a.gate != nullptr && ((*a.gate == 0) != (a.gate_run_if_zero != 0))) return;  // the other CG kernel does the work
   __shared__ double red[96];
   __shared__ int s_k;
   const int n = a.md.n, m = a.md.m, ld = a.md.ld;
@@ -1428,13 +1407,9 @@ static double squared_threshold(double tol) {
   return t;
 }
 
-int launch_cg(cudaStream_t s, const CgArgs& a_in, int num_sms, int* variant) {
-  if (a_in.N == 0) return 0;
+static int launch_cg_general(cudaStream_t s, const CgArgs& a_in, int num_sms, int* variant) {
   if (a_in.precond == 2 && !(resident_smem_bytes(a_in.md) <= 227 * 1024 && a_in.md.n <= 512 * 9)) return -2;
   CgArgs a = a_in;
-  a.tol2 = squared_threshold(a.tol);
-  cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
-  cudaMemsetAsync(a.fail_flag, 0, sizeof(int), s);
   const int n = a.md.n;
   const bool fits = resident_smem_bytes(a.md) <= 227 * 1024 && n <= 512 * 9;  // 512 x 9 rows is the largest strip shape
   const char* force = std::getenv("MSGPU_CG_VARIANT");  // "global" forces the streaming kernel (tests)
@@ -1505,6 +1480,45 @@ int launch_cg(cudaStream_t s, const CgArgs& a_in, int num_sms, int* variant) {
   }
   k_cg_global<BT><<<grid, BT, 0, s>>>(a, g_workspace);
   return 1;
+}
+
+// Dispatch.  Systems whose matrix is class-uniform (kernels_cg_stencil.cu) take the stencil kernel; whether they
+// are is decided ON THE DEVICE by the compression kernel unless the caller already knows (stencil_hint): both CG
+// kernels are launched back to back behind the flag and one of them returns at once.
+int launch_cg(cudaStream_t s, const CgArgs& a_in, int num_sms, int* variant) {
+  if (a_in.N == 0) return 0;
+  if (a_in.precond == 2 && !(resident_smem_bytes(a_in.md) <= 227 * 1024 && a_in.md.n <= 512 * 9)) return -2;
+  CgArgs a = a_in;
+  a.tol2 = squared_threshold(a.tol);
+  a.gate = nullptr;
+  cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
+  cudaMemsetAsync(a.fail_flag, 0, sizeof(int), s);
+  int launched = 0, stencil_variant = 0;
+  const char* st_env = std::getenv("MSGPU_CG_STENCIL");  // "0": never take the class-compressed kernel (A/B, tests)
+  if (a.stencil_ws != nullptr && a.stencil_bad != nullptr && a.precond == 0 && a.stencil_hint != 2 &&
+      !(st_env && st_env[0] == '0') && stencil_supported(a.md, a.dirichlet)) {
+    cudaMemsetAsync(a.stencil_bad, 0, sizeof(int), s);
+    launched += launch_stencil_compress(s, a, a.stencil_hint == 0);
+    CgArgs st = a;
+    st.gate = a.stencil_bad;
+    st.gate_run_if_zero = 1;
+    const int r = launch_cg_stencil(s, st, num_sms);
+    if (r > 0) {
+      launched += r;
+      stencil_variant = 5;
+      if (a.stencil_hint == 1) {
+        if (variant) *variant = 5;
+        return launched;
+      }
+      a.gate = a.stencil_bad;  // the general kernel below runs only if the flag went up
+      a.gate_run_if_zero = 0;
+    }
+  }
+  int general_variant = 0;
+  const int r = launch_cg_general(s, a, num_sms, &general_variant);
+  if (r < 0) return r;
+  if (variant) *variant = stencil_variant ? (stencil_variant | (general_variant << 8)) : general_variant;
+  return launched + r;
 }
 
 int launch_coupling(cudaStream_t s, const CouplingArgs& a) {

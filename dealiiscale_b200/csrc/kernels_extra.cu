@@ -325,6 +325,7 @@ int parabolic_assemble(msgpu_ctx* ctx, double dt, double t) {
     CKX(cudaMemcpyAsync(ctx->d_diag, sys.data(), sizeof(double) * sys.size(), cudaMemcpyHostToDevice, ctx->stream));
     CKX(cudaStreamSynchronize(ctx->stream));
     ctx->parabolic_dt = dt;
+    ctx->stencil_hint = 0;  // another matrix
   }
   int rc = build_tables_at(ctx, t);  // data.set_time(t) (time_manager.cpp:66)
   if (rc) return rc;

@@ -57,7 +57,7 @@ void free_all(msgpu_ctx* ctx) {
                   ctx->d_q1pt, ctx->d_q1wt,  ctx->d_cell, ctx->d_face, ctx->d_diag,   ctx->d_b0,     ctx->d_jw,
                   ctx->d_edge, ctx->d_bv,    ctx->d_b,   ctx->d_x,    ctx->d_xold,   ctx->d_u,      ctx->d_w,
                   ctx->d_c,    ctx->d_res,   ctx->d_iters, ctx->d_flags, ctx->d_err,  ctx->d_mass,   ctx->d_macro,
-                  ctx->d_lumped, ctx->d_cellred, ctx->d_eq_pt, ctx->d_eq_wt};
+                  ctx->d_lumped, ctx->d_cellred, ctx->d_eq_pt, ctx->d_eq_wt, ctx->d_stencil};
   for (void* p : ptrs)
     if (p) cudaFree(p);
 }
@@ -275,6 +275,7 @@ int msgpu_set_scalars(msgpu_ctx* ctx, const double* values, int n) {
   if (!ctx || !values || n < 0 || n > MSGPU_MAX_SCALARS) return MSGPU_ERR_INVALID;
   for (int i = 0; i < n; ++i) ctx->scalars[i] = values[i];
   ctx->n_scalars = n;
+  ctx->stencil_hint = 0;  // the Robin terms of the matrices change with the scalars
   return MSGPU_OK;
 }
 
@@ -390,6 +391,8 @@ int msgpu_setup(msgpu_ctx* ctx) {
   if ((rc = dev_alloc(ctx, &ctx->d_iters, static_cast<size_t>(N)))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_flags, static_cast<size_t>(4)))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_err, 2 * static_cast<size_t>(N)))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_stencil, (shared_matrix ? 1 : static_cast<size_t>(N)) * STENCIL_TABLE))) return rc;
+  ctx->stencil_hint = 0;
 
   CK(cudaMemcpyAsync(ctx->d_xy, ctx->xy.data(), 2 * sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_coord0, c0.data(), sizeof(double) * md.P, cudaMemcpyHostToDevice, ctx->stream));
@@ -552,6 +555,10 @@ int msgpu_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int precond, int* it
     a.res = ctx->d_res;
     a.work_counter = ctx->d_flags + FLAG_COUNTER;
     a.fail_flag = ctx->d_flags + FLAG_CGFAIL;
+    a.stencil_ws = ctx->d_stencil;
+    a.stencil_bad = ctx->d_flags + FLAG_STENCIL_BAD;
+    a.stencil_hint = ctx->stencil_hint;
+    a.dirichlet = ctx->desc.problem == MSGPU_ELLIPTIC ? 1 : 0;
     int variant = 0;
     int l = launch_cg(ctx->stream, a, ctx->num_sms, &variant);
     if (l == -2)
@@ -568,6 +575,13 @@ int msgpu_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int precond, int* it
   if (final_res)
     CK(cudaMemcpyAsync(final_res, ctx->d_res, sizeof(double) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if ((ctx->cg_variant & 0xff) == 5 && (ctx->cg_variant >> 8) != 0) {
+    // both CG kernels were launched behind the device flag: it tells which one did the work, and the next
+    // solves of this (unchanged) matrix launch only that one
+    const bool uniform = flags[FLAG_STENCIL_BAD] == 0;
+    ctx->stencil_hint = uniform ? 1 : 2;
+    ctx->cg_variant = uniform ? 5 : (ctx->cg_variant >> 8);
+  }
   long long total = 0;
   for (int v : ctx->h_iters) total += v;
   ctx->cg_iterations_total = total;
