@@ -14,21 +14,24 @@
 // The entries are the assembled doubles themselves: the matrix-vector product is the one with the explicit matrix
 // (only the order of the nine additions of a row and of the reduction trees differs from k_cg_strip_tmem).
 //
-// With the matrix gone from tensor memory the SM has room for TWO systems, which is what the general kernel lacks
-// (45 % of a CG step is two block reductions and a scalar chain with nothing else resident to hide them):
-//   * a thread owns a strip of K consecutive nodes of ONE mesh column (S strips per column, S*K >= nodes per axis;
-//     the last strip is anchored at the end of the column, so both boundary nodes of a column sit at compile-time
-//     positions - row 0 of the first strip, row K-1 of the last - and the S*K - mp rows the last strip shares with
-//     its neighbour are computed twice, bit-identically, and counted once);
-//     the search direction d sits in registers (own strip) and in shared memory (neighbours: column pitch P with a
-//     zero pad that doubles as the missing neighbours of boundary nodes, so there are no index tests);
-//   * x, g and h = A d live in TENSOR MEMORY, 6K columns per thread, streamed through registers four rows at a time
-//     (tcgen05.ld / tcgen05.st, SASS LDTM / STTM) - lane-private storage behind its own datapath;
-//   * the nine couplings of the thread's column class are registers; the two boundary rows of a column (first row
-//     of the first strip, last live row of the last strip) take theirs from the class table in shared memory;
-//   * <= 88 registers x 352 threads and 256 tensor-memory columns per CTA: two CTAs per SM.
-// Thread t -> (strip s = t / mp, column ix = t % mp): a warp holds strips of the same s (but for one seam), so the
-// "does this warp hold a boundary row" tests are warp-uniform and nothing diverges around the .aligned tcgen05 ops.
+// With the matrix gone there is nothing left to stream per CG step but the neighbours of the search direction, and
+// the SpMV - 1400 of the 3030 cycles of a k_cg_strip_tmem step, bound by the tensor-memory reads - becomes FP64 work
+// on registers, provided the shared-memory traffic of the neighbour exchange stays below it (one wavefront per cycle
+// and SM; 13 x 1 strips needed 1543 wavefronts per step, see profiles/r2_a_stencil_tmem_variant.md):
+//   * a thread owns a TILE of W = 3 adjacent mesh columns x KR = 4 consecutive nodes: 18 neighbour loads and 12 stores
+//     per 12 nodes.  Tile rows: S strips per column, the last strip anchored at the end of the column, so the boundary
+//     nodes of a column sit at compile-time positions (row 0 of the first strip, row KR-1 of the last) and the
+//     S*KR - mp rows the last strip shares with its neighbour are computed twice, bit-identically, and counted once.
+//     Tile columns past the mesh (mp not a multiple of 3) compute zeros;
+//   * x, g, h = A d and the own tile of d are registers; d is also in shared memory for the neighbours (column pitch
+//     P with a zero pad that doubles as the missing neighbours of boundary nodes, so there are no index tests);
+//   * every coupling is a register: k_stencil_compress checks that the class table has the form
+//         self(cx, cy),  vertical(cx),  horizontal(cy),  two diagonal values
+//     (what a symmetric operator with per-system constant coefficients and boundary terms along the faces gives), so a
+//     thread needs 9 + 3 + 2 values of its own and 3 that are the same for everybody;
+//   * one CTA of <= 384 threads per SM for 65 x 65 nodes, more for smaller meshes.
+// Thread t -> (strip s = t / TC, tile column tc = t % TC): adjacent lanes own adjacent tiles, shared-memory accesses
+// of a warp are 3 P doubles apart (P odd: conflict free).
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -44,304 +47,130 @@ namespace {
 using cgc::l2_prefetch_bulk;
 using cgc::warp_sum;
 
-constexpr int ST_MAX_THREADS = 352;  // 11 warps; two CTAs of 88 registers per thread fill the register file
-constexpr int ST_RED = 16;           // slots of one reduction buffer (>= warps per CTA; a power of two)
+constexpr int ST_MAX_THREADS = 256;  // 8 warps x 255 registers
+constexpr int ST_RED = 16;           // slots of one reduction buffer (>= warps per CTA)
+constexpr int ST_W = 3, ST_KR = 6;   // tile of a thread: columns x rows
 
 struct StencilPlan {
   int mp;     // nodes per axis of the block the CG runs on: m, or m - 2 when Dirichlet rows are left out
   int off;    // first mesh line of that block (0 | 1)
-  int K;      // rows per thread
-  int S;      // strips per mesh column
+  int TC;     // tiles per mesh row: ceil(mp / ST_W)
+  int S;      // strips per mesh column: ceil(mp / ST_KR)
   int P;      // pitch of a column of d in shared memory (odd, >= mp + 1)
-  int ov;     // rows the last strip of a column shares with the strip before it (S*K - mp <= 3)
+  int ov;     // rows the last strip of a column shares with the strip before it (S*ST_KR - mp)
   int block;  // CTA size
-  int alloc;  // tensor-memory columns per CTA (power of two)
-  int cw;     // tensor-memory columns per warp
 };
 
-bool make_plan(const MeshDims& md, int dirichlet, StencilPlan& best) {
+bool make_plan(const MeshDims& md, int dirichlet, StencilPlan& p) {
   const int off = dirichlet ? 1 : 0, mp = md.m - 2 * off;
   if (mp < 24) return false;  // small systems: several CTAs of the plain strip kernel per SM do as well
-  double best_eff = 0.0;
-  for (int K = 13; K >= 9; --K) {
-    const int S = (mp + K - 1) / K, ov = S * K - mp, threads = S * mp;
-    if (ov > 3 || threads > ST_MAX_THREADS || S < 2) continue;
-    const int block = (threads + 31) & ~31;
-    const double eff = static_cast<double>(mp) * mp / (static_cast<double>(block) * K);
-    if (eff <= best_eff) continue;
-    StencilPlan p;
-    p.mp = mp;
-    p.off = off;
-    p.K = K;
-    p.S = S;
-    p.P = (mp + 1) | 1;
-    p.ov = ov;
-    p.block = block;
-    p.cw = 6 * K;
-    const int slots = (block / 32 + 3) / 4;
-    int alloc = 32;
-    while (alloc < slots * p.cw) alloc *= 2;
-    if (alloc > 512) continue;
-    p.alloc = alloc;
-    best = p;
-    best_eff = eff;
-  }
-  return best_eff > 0.0;
+  p.mp = mp;
+  p.off = off;
+  p.TC = (mp + ST_W - 1) / ST_W;
+  p.S = (mp + ST_KR - 1) / ST_KR;
+  if (p.TC * p.S > ST_MAX_THREADS) return false;
+  p.P = (mp + 1) | 1;
+  p.ov = p.S * ST_KR - mp;
+  p.block = (p.TC * p.S + 31) & ~31;
+  return true;
 }
 
-size_t plan_smem_bytes(const StencilPlan& p) {
-  const size_t dvlen = (static_cast<size_t>(2) + static_cast<size_t>(p.mp + 4) * p.P + 1) & ~static_cast<size_t>(1);
-  return (dvlen + 3 * ST_RED + STENCIL_TABLE + 1) * sizeof(double);
+// dv[ix * P + iy] for ix in [-1, mp + 5]: one guard column in front, tile columns past the mesh and the tile of idle
+// threads behind; 2 doubles in front of everything for the (-1, -1) corner of the first tile
+size_t plan_dv_len(const StencilPlan& p) {
+  return (static_cast<size_t>(2) + static_cast<size_t>(p.mp + 7) * p.P + 1) & ~static_cast<size_t>(1);
 }
-
-// ------------------------------------------------------------------------------------------------
-// tensor-memory vectors: ND doubles = 2 ND columns of one lane
-template <int ND>
-struct TV {
-  uint32_t r[2 * ND];
-};
-template <int ND>
-__device__ __forceinline__ double tv_get(const TV<ND>& q, int i) {
-  return __hiloint2double(static_cast<int>(q.r[2 * i + 1]), static_cast<int>(q.r[2 * i]));
-}
-
-// Asynchronous loads; tm_wait* takes the destination registers as in/out operands so that no use of them can be
-// scheduled before the wait (tensor memory is not aliased by any pointer: no "memory" clobber needed).
-template <int ND>
-__device__ __forceinline__ void tm_ld(uint32_t a, TV<ND>& q) {
-  if constexpr (ND == 4) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-                 : "=r"(q.r[0]), "=r"(q.r[1]), "=r"(q.r[2]), "=r"(q.r[3]), "=r"(q.r[4]), "=r"(q.r[5]), "=r"(q.r[6]),
-                   "=r"(q.r[7])
-                 : "r"(a));
-  } else if constexpr (ND == 2) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
-                 : "=r"(q.r[0]), "=r"(q.r[1]), "=r"(q.r[2]), "=r"(q.r[3])
-                 : "r"(a));
-  } else {
-    static_assert(ND == 1, "chunk size");
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n" : "=r"(q.r[0]), "=r"(q.r[1]) : "r"(a));
-  }
-}
-template <int ND>
-__device__ __forceinline__ void tm_wait(TV<ND>& q) {
-  if constexpr (ND == 4) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-                 : "+r"(q.r[0]), "+r"(q.r[1]), "+r"(q.r[2]), "+r"(q.r[3]), "+r"(q.r[4]), "+r"(q.r[5]), "+r"(q.r[6]),
-                   "+r"(q.r[7]));
-  } else if constexpr (ND == 2) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : "+r"(q.r[0]), "+r"(q.r[1]), "+r"(q.r[2]), "+r"(q.r[3]));
-  } else {
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : "+r"(q.r[0]), "+r"(q.r[1]));
-  }
-}
-template <int ND>
-__device__ __forceinline__ void tm_wait3(TV<ND>& a, TV<ND>& b, TV<ND>& c) {
-  if constexpr (ND == 4) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-                 : "+r"(a.r[0]), "+r"(a.r[1]), "+r"(a.r[2]), "+r"(a.r[3]), "+r"(a.r[4]), "+r"(a.r[5]), "+r"(a.r[6]),
-                   "+r"(a.r[7]), "+r"(b.r[0]), "+r"(b.r[1]), "+r"(b.r[2]), "+r"(b.r[3]), "+r"(b.r[4]), "+r"(b.r[5]),
-                   "+r"(b.r[6]), "+r"(b.r[7]), "+r"(c.r[0]), "+r"(c.r[1]), "+r"(c.r[2]), "+r"(c.r[3]), "+r"(c.r[4]),
-                   "+r"(c.r[5]), "+r"(c.r[6]), "+r"(c.r[7]));
-  } else if constexpr (ND == 2) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-                 : "+r"(a.r[0]), "+r"(a.r[1]), "+r"(a.r[2]), "+r"(a.r[3]), "+r"(b.r[0]), "+r"(b.r[1]), "+r"(b.r[2]),
-                   "+r"(b.r[3]), "+r"(c.r[0]), "+r"(c.r[1]), "+r"(c.r[2]), "+r"(c.r[3]));
-  } else {
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-                 : "+r"(a.r[0]), "+r"(a.r[1]), "+r"(b.r[0]), "+r"(b.r[1]), "+r"(c.r[0]), "+r"(c.r[1]));
-  }
-}
-// Asynchronous store of ONE double (two columns); tm_st_wait before the same thread reads the columns back.  Wider
-// stores want their 4 / 8 source registers consecutive and aligned, which costs more register moves than the extra
-// store instructions do (ncu, round 2: 190 of 680 instructions per CG step were such moves).
-__device__ __forceinline__ void tm_st1(uint32_t a, double v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};\n" ::"r"(a), "r"(__double2loint(v)),
-               "r"(__double2hiint(v)));
-}
-__device__ __forceinline__ void tm_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n"); }
-
-// f(integral_constant<int, ND>, j0) for the chunks [j0, j0 + ND) of a strip of K rows: fours, then a pair, then one
-template <int K, class F>
-__device__ __forceinline__ void for_each_chunk(F&& f) {
-#pragma unroll
-  for (int c = 0; c < K / 4; ++c) f(std::integral_constant<int, 4>{}, 4 * c);
-  if constexpr ((K % 4) >= 2) f(std::integral_constant<int, 2>{}, K - (K % 4));
-  if constexpr ((K % 2) == 1) f(std::integral_constant<int, 1>{}, K - 1);
-}
+size_t plan_smem_bytes(const StencilPlan& p) { return (plan_dv_len(p) + 3 * ST_RED + STENCIL_TABLE + 1) * sizeof(double); }
 
 // Sum over the CTA, result in every thread: warp partials into `red` (ST_RED slots; the slots of warps the CTA does
-// not have stay zero), one barrier, then every warp adds them with one more shuffle tree (fixed order:
-// bit-reproducible, and 4 additions per thread instead of 11 - the FP64 pipe is what this kernel runs out of).
+// not have stay zero), one barrier, then every thread adds the first twelve in one fixed tree (bit-reproducible; a
+// tree of additions has a shorter dependency chain than a second round of shuffles, and with one system per SM the
+// step is bound by such chains, not by the FP64 pipe).
 // `red` must not be written again before the next barrier that follows this call (callers rotate three buffers).
 __device__ __forceinline__ double block_sum12(double v, double* red) {
   v = warp_sum(v);
-  const int lane = threadIdx.x & 31;
-  if (lane == 0) red[threadIdx.x >> 5] = v;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  double t = red[lane & 15];  // slots 12..15 are zero padding
+  double t[12];
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-  return t;
+  for (int i = 0; i < 12; i += 2) {
+    const double2 q = *reinterpret_cast<const double2*>(red + i);
+    t[i] = q.x;
+    t[i + 1] = q.y;
+  }
+  return (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]))) + ((t[8] + t[9]) + (t[10] + t[11]));
 }
 
-// One matrix row: nine products, one chain, fixed order (a thread has K independent rows in flight, and an extra
-// addition per row to join two chains is FP64 work this kernel cannot afford).  c: self, up, down, right-down, right,
-// right-up, left-up, left, left-down.
-__device__ __forceinline__ double row9(const double* __restrict__ c, double self, double above, double below, double la,
-                                       double lb, double lc, double ra, double rb, double rc) {
-  double s = c[0] * self;
-  s += c[1] * above;
-  s += c[2] * below;
-  s += c[3] * ra;
-  s += c[6] * lc;
-  s += c[4] * rb;
-  s += c[7] * lb;
-  s += c[5] * rc;
-  s += c[8] * la;
+// One matrix row: nine products, one chain, fixed order: self, up, down, right-down, left-up, right, left, right-up,
+// left-down (a thread has 12 independent rows in flight; joining two chains would cost one more FP64 addition per row).
+__device__ __forceinline__ double stencil_row(double cself, double cv, double ch, double cda, double cdb, double self,
+                                              double above, double below, double l_dn, double l_md, double l_up,
+                                              double r_dn, double r_md, double r_up) {
+  double s = cself * self;
+  s += cv * above;
+  s += cv * below;
+  s += cda * r_dn;
+  s += cda * l_up;
+  s += ch * r_md;
+  s += ch * l_md;
+  s += cdb * r_up;
+  s += cdb * l_dn;
   return s;
 }
 
-// The same row for an inner node of a column: in a class-uniform symmetric matrix its up / down couplings coincide
-// (c1) and so do the three pairs of couplings to the right and left columns (cs[0..2] = right-down | left-up,
-// right | left, right-up | left-down) - k_stencil_compress checks exactly that - so five registers carry the row.
-// On the first / last column the side that does not exist multiplies the zero guard column.
-__device__ __forceinline__ double row5(double c0, double c1, const double (&cs)[3], double self, double above,
-                                       double below, double la, double lb, double lc, double ra, double rb, double rc) {
-  double s = c0 * self;
-  s += c1 * above;
-  s += c1 * below;
-  s += cs[0] * ra;
-  s += cs[0] * lc;
-  s += cs[1] * rb;
-  s += cs[1] * lb;
-  s += cs[2] * rc;
-  s += cs[2] * la;
-  return s;
-}
-
-template <int K>
-__global__ void __launch_bounds__(ST_MAX_THREADS, 2)
+__global__ void __launch_bounds__(ST_MAX_THREADS, 1)
     k_cg_stencil(const __grid_constant__ CgArgs a, const __grid_constant__ StencilPlan p) {
   if (a.gate != nullptr && ((*a.gate == 0) != (a.gate_run_if_zero != 0))) return;  // the other kernel does the work
   constexpr bool FAST = MSGPU_FAST_SCALARS;
+  constexpr int W = ST_W, KR = ST_KR;
   extern __shared__ __align__(16) double sm[];
   __shared__ int s_k, s_next;
-  __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-  const int mp = p.mp, P = p.P, S = p.S, m = a.md.m, n = a.md.n, off = p.off, ov = p.ov;
-  const int dvlen = (2 + (mp + 4) * P + 1) & ~1;
-  double* const dv = sm + 2 + P;   // dv[ix * P + iy], ix in [-1, mp + 2]; everything nobody writes stays zero
+  const int mp = p.mp, P = p.P, m = a.md.m, n = a.md.n, off = p.off, ov = p.ov;
+  const int dvlen = (2 + (mp + 7) * P + 1) & ~1;
+  double* const dv = sm + 2 + P;   // everything nobody writes stays zero
   double* const red = sm + dvlen;  // 3 x ST_RED, 16-byte aligned
   double* const tab = red + 3 * ST_RED;
 
-  const int s = tid / mp;
-  const bool live = s < S;  // threads past S*mp idle on column mp + 1: zeros there and on both sides, so h = 0
-  const int ix = live ? tid - s * mp : mp + 1;
-  const bool first = live && s == 0, last = live && s == S - 1;
-  double* const dvc = dv + ix * P + (live ? (last ? mp - K : s * K) : 0);
-  const int cx = ix == 0 ? 0 : (ix == mp - 1 ? 2 : 1);
-  // class rows of the first / last node of this strip: the inner class unless the strip touches the end of the column
-  const double* const tab_lo = tab + (cx * 3 + (first ? 0 : 1)) * 9;
-  const double* const tab_hi = tab + (cx * 3 + (last ? 2 : 1)) * 9;
+  const int s = tid / p.TC;
+  const bool live = s < p.S;  // idle threads sit on columns mp + 2 .. mp + 4: zeros there and on both sides
+  const int ix0 = live ? (tid - s * p.TC) * W : mp + 2;
+  const bool first = live && s == 0, last = live && s == p.S - 1;
+  double* const dvt = dv + ix0 * P + (live ? (last ? mp - KR : s * KR) : 0);  // node (0, 0) of the tile
+  bool col_live[W];  // tile columns past the mesh compute zeros and write nothing
+#pragma unroll
+  for (int c = 0; c < W; ++c) col_live[c] = live && ix0 + c < mp;
   // rows [0, ov) of a last strip belong to the strip before it: same arithmetic there and here, counted there
-  auto shadow = [&](int j) -> bool { return j < 3 && last && j < ov; };
+  auto shadow = [&](int j) -> bool { return j < KR - 1 && last && j < ov; };
 
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
-                     static_cast<uint32_t>(__cvta_generic_to_shared(&s_tmem))),
-                 "r"(static_cast<uint32_t>(p.alloc)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
-  }
   for (int i = tid; i < dvlen + 3 * ST_RED + STENCIL_TABLE + 1; i += blockDim.x) sm[i] = 0.0;
-  asm volatile("tcgen05.fence::before_thread_sync;\n");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;\n");
-  // lane quadrant of this warp in bits 31:16, column block of this warp in bits 15:0
-  const uint32_t xcol = s_tmem + ((static_cast<uint32_t>(warp & 3) * 32u) << 16) +
-                        static_cast<uint32_t>(warp >> 2) * static_cast<uint32_t>(p.cw);
-  const uint32_t gcol = xcol + 2u * K, hcol = xcol + 4u * K;
 
-  double dl[K];      // own strip of the search direction
-  double c0, c1;     // couplings of an inner node of this thread's column: self, up = down
-  double cs[3];      // ... and to the neighbouring columns (the same for every thread)
-
-  // h = A d for this strip -> tensor memory; returns the strip's part of d.h
-  auto spmv = [&]() -> double {
-    double la = dvc[-P - 1], lb = dvc[-P];
-    double ra = dvc[P - 1], rb = dvc[P];
-    double below = dvc[-1];
-    double acc[2] = {0.0, 0.0};
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      const double lc = dvc[-P + j + 1], rc = dvc[P + j + 1];
-      const double above = (j + 1 < K) ? dl[j + 1] : dvc[K];
-      double h;
-      if (j == 0)
-        h = row9(tab_lo, dl[j], above, below, la, lb, lc, ra, rb, rc);
-      else if (j == K - 1)
-        h = row9(tab_hi, dl[j], above, below, la, lb, lc, ra, rb, rc);
-      else
-        h = row5(c0, c1, cs, dl[j], above, below, la, lb, lc, ra, rb, rc);
-      acc[j & 1] += dl[j] * (shadow(j) ? 0.0 : h);
-      tm_st1(hcol + 2u * j, h);
-      la = lb;
-      lb = lc;
-      ra = rb;
-      rb = rc;
-      below = dl[j];
-    }
-    tm_st_wait();
-    return acc[0] + acc[1];
-  };
-
-  // x += alpha d, g += alpha h; returns the strip's part of g.g
-  auto update = [&](double alpha) -> double {
-    double acc[2] = {0.0, 0.0};
-    for_each_chunk<K>([&](auto nd, int j0) {
-      constexpr int ND = decltype(nd)::value;
-      TV<ND> qh, qg, qx;
-      tm_ld<ND>(hcol + 2u * j0, qh);
-      tm_ld<ND>(gcol + 2u * j0, qg);
-      tm_ld<ND>(xcol + 2u * j0, qx);
-      tm_wait3<ND>(qh, qg, qx);
-#pragma unroll
-      for (int i = 0; i < ND; ++i) {
-        const double xo = tv_get<ND>(qx, i) + alpha * dl[j0 + i];
-        const double go = tv_get<ND>(qg, i) + alpha * tv_get<ND>(qh, i);
-        acc[(j0 + i) & 1] += go * (shadow(j0 + i) ? 0.0 : go);
-        tm_st1(xcol + 2u * (j0 + i), xo);
-        tm_st1(gcol + 2u * (j0 + i), go);
-      }
-    });
-    tm_st_wait();
-    return acc[0] + acc[1];
-  };
-
-  // d = beta d - g, own strip to shared memory
-  auto direction = [&](double beta) {
-    for_each_chunk<K>([&](auto nd, int j0) {
-      constexpr int ND = decltype(nd)::value;
-      TV<ND> qg;
-      tm_ld<ND>(gcol + 2u * j0, qg);
-      tm_wait<ND>(qg);
-#pragma unroll
-      for (int i = 0; i < ND; ++i) {
-        dl[j0 + i] = beta * dl[j0 + i] - tv_get<ND>(qg, i);
-        if (live && !shadow(j0 + i)) dvc[j0 + i] = dl[j0 + i];
-      }
-    });
-  };
+  double xx[W][KR], gg[W][KR], dl[W][KR], hh[W][KR];  // solution, residual, search direction, A d: this thread's tile
+  double cself[W][3];  // diagonal entries of the tile's columns: row 0, inner rows, row KR-1 of the tile
+  double cvert[W];     // up / down coupling of the tile's columns
+  double chor[3];      // left / right coupling for row 0, inner rows, row KR-1 of the tile
+  double cda, cdb;     // diagonal couplings: right-down | left-up, right-up | left-down (the same for every thread)
 
   // the block the CG runs on, between global memory (mesh ordering, coalesced) and the padded columns of dv
   auto stage_in = [&](const double* __restrict__ src) {
     for (int c = warp; c < mp; c += nw)
       for (int i = lane; i < mp; i += 32) dv[c * P + i] = src[static_cast<size_t>(c + off) * m + (i + off)];
   };
+// every node (c, j) of the tile, fully unrolled (the loops sit at their place of use: a lambda called from several
+// places does not always get unrolled, and a loop that is not turns the register tiles into local memory)
+#define MSGPU_TILE(c, j)                                \
+  _Pragma("unroll") for (int e_ = 0; e_ < W * KR; ++e_) \
+    if (const int c = e_ / KR; true)                    \
+      if (const int j = e_ % KR; true)
+// own tile of d (or x) to shared memory; rows shared with the strip before: the owner writes
+#define MSGPU_PUBLISH(v) MSGPU_TILE(c, j) if (col_live[c] && !shadow(j)) dvt[c * P + j] = v[c][j]
 
   // The queue is read one system ahead: the right-hand side and the start vector of the NEXT system are pulled
   // into L2 by bulk prefetches while this one is being solved.
   if (tid == 0) s_next = atomicAdd(a.work_counter, 1);
+#ifdef MSGPU_STENCIL_STAMPS
+  long long st_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0}, st_its = 0;  // debug build: clock64 cycles per phase
+#endif
   for (;;) {
     __syncthreads();
     if (tid == 0) {
@@ -365,82 +194,167 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 2)
       tab[tid] = __ldg(a.stencil_ws + (a.diag_stride != 0 ? static_cast<size_t>(k) * STENCIL_TABLE : 0) + tid);
     stage_in(xk);
     __syncthreads();
-    c0 = live ? tab[(cx * 3 + 1) * 9 + 0] : 0.0;
-    c1 = live ? tab[(cx * 3 + 1) * 9 + 1] : 0.0;
+    // couplings of this tile from the class table T[cx][cy][e] (form checked by k_stencil_compress)
+    {
+      const int cy_lo = first ? 0 : 1, cy_hi = last ? 2 : 1;
 #pragma unroll
-    for (int e = 0; e < 3; ++e) cs[e] = tab[(1 * 3 + 1) * 9 + 3 + e];
-#pragma unroll
-    for (int j = 0; j < K; ++j) dl[j] = dvc[j];  // idle threads read the zero pad
-#pragma unroll
-    for (int j = 0; j < K; ++j) tm_st1(xcol + 2u * j, dl[j]);
-    // ---- g = A x - b
-    spmv();
-    __syncthreads();  // everybody is done with x in dv
-    stage_in(bk);
-    __syncthreads();
-    double acc0[2] = {0.0, 0.0};
-    for_each_chunk<K>([&](auto nd, int j0) {
-      constexpr int ND = decltype(nd)::value;
-      TV<ND> qh;
-      tm_ld<ND>(hcol + 2u * j0, qh);
-      tm_wait<ND>(qh);
-#pragma unroll
-      for (int i = 0; i < ND; ++i) {
-        const double go = tv_get<ND>(qh, i) - dvc[j0 + i];
-        acc0[(j0 + i) & 1] += go * (shadow(j0 + i) ? 0.0 : go);
-        tm_st1(gcol + 2u * (j0 + i), go);
+      for (int c = 0; c < W; ++c) {
+        const int ix = ix0 + c, cx = ix == 0 ? 0 : (ix == mp - 1 ? 2 : 1);
+        cself[c][0] = col_live[c] ? tab[(cx * 3 + cy_lo) * 9] : 0.0;
+        cself[c][1] = col_live[c] ? tab[(cx * 3 + 1) * 9] : 0.0;
+        cself[c][2] = col_live[c] ? tab[(cx * 3 + cy_hi) * 9] : 0.0;
+        cvert[c] = col_live[c] ? tab[(cx * 3 + 1) * 9 + 1] : 0.0;
       }
-    });
-    tm_st_wait();
-    double res = sqrt(block_sum12(acc0[0] + acc0[1], red));
-    int it = 0;
-    bool ok = res <= a.tol;
-    if (!ok) {
-      // the barrier inside block_sum12 separates the reads of b from this overwrite of dv
-      direction(0.0);  // d = -g (0 * x - g)
-      double gh = res * res;
-      double rgh = FAST ? 1.0 / gh : 0.0;
-      for (;;) {
-        ++it;
-        __syncthreads();
-        const double dh = block_sum12(spmv(), red + ST_RED);
-        const double alpha = gh / dh;
-        const double s2 = block_sum12(update(alpha), red + 2 * ST_RED);
-        double gh_new;
-        if (FAST) {
-          res = s2;
-          gh_new = s2;
-          if (s2 <= a.tol2) {
-            ok = true;
-            break;
-          }
-        } else {
-          res = sqrt(s2);
-          gh_new = res * res;
-          if (res <= a.tol) {
-            ok = true;
-            break;
-          }
-        }
-        if (it >= a.max_it || s2 != s2) break;
-        const double beta = FAST ? gh_new * rgh : gh_new / gh;
-        gh = gh_new;
-        if (FAST) rgh = 1.0 / gh;
-        direction(beta);
-      }
-      if (FAST) res = sqrt(res);
+      chor[0] = tab[(1 * 3 + cy_lo) * 9 + 4];
+      chor[1] = tab[(1 * 3 + 1) * 9 + 4];
+      chor[2] = tab[(1 * 3 + cy_hi) * 9 + 4];
+      cda = tab[(1 * 3 + 1) * 9 + 3];
+      cdb = tab[(1 * 3 + 1) * 9 + 5];
     }
-    // ---- write the solution back: tensor memory -> padded columns -> mesh ordering (coalesced)
-    __syncthreads();
-    for_each_chunk<K>([&](auto nd, int j0) {
-      constexpr int ND = decltype(nd)::value;
-      TV<ND> qx;
-      tm_ld<ND>(xcol + 2u * j0, qx);
-      tm_wait<ND>(qx);
+    MSGPU_TILE(c, j) {
+      xx[c][j] = dvt[c * P + j];  // idle threads and columns past the mesh read the zero pad
+      dl[c][j] = xx[c][j];
+      gg[c][j] = 0.0;
+    }
+    // The first pass through the loop computes g = A x - b (d = x is in shared memory already), the following
+    // ones are CG steps: one place of use for the SpMV.
+    bool start = true, ok = false;
+    int it = 0;
+    double res = 0.0, gh = 0.0, rgh = 0.0;
+#ifdef MSGPU_STENCIL_STAMPS
+    long long st_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, st_c = clock64();
+#define MSGPU_STAMP(i)                                    \
+  {                                                       \
+    const long long now_ = clock64();                     \
+    st_t[i] += now_ - st_c;                               \
+    st_c = now_;                                          \
+  }
+#else
+#define MSGPU_STAMP(i)
+#endif
+    for (;;) {
+      __syncthreads();
+      MSGPU_STAMP(0)  // closing barrier of the previous step
+      // ---- hh = A dl for this tile, and the tile's part of d.h
+      double dh_part;
+      {
+        double L[KR + 2], R[KR + 2], B[W], A[W];
 #pragma unroll
-      for (int i = 0; i < ND; ++i)
-        if (live && !shadow(j0 + i)) dvc[j0 + i] = tv_get<ND>(qx, i);
-    });
+        for (int j = 0; j < KR + 2; ++j) {
+          L[j] = dvt[-P + j - 1];
+          R[j] = dvt[W * P + j - 1];
+        }
+#pragma unroll
+        for (int c = 0; c < W; ++c) {
+          B[c] = dvt[c * P - 1];
+          A[c] = dvt[c * P + KR];
+        }
+        // value of d at tile position (c, j), c in [-1, W], j in [-1, KR]
+        auto D = [&](int c, int j) -> double {
+          if (c < 0) return L[j + 1];
+          if (c >= W) return R[j + 1];
+          if (j < 0) return B[c];
+          if (j >= KR) return A[c];
+          return dl[c][j];
+        };
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        MSGPU_TILE(c, j) {
+          const int rc = j == 0 ? 0 : (j == KR - 1 ? 2 : 1);
+          double h = stencil_row(cself[c][rc], cvert[c], chor[rc], cda, cdb, D(c, j), D(c, j + 1), D(c, j - 1),
+                                 D(c - 1, j - 1), D(c - 1, j), D(c - 1, j + 1), D(c + 1, j - 1), D(c + 1, j),
+                                 D(c + 1, j + 1));
+          if (c > 0) h = col_live[c] ? h : 0.0;
+          hh[c][j] = h;
+          acc[(c * KR + j) & 3] += dl[c][j] * (shadow(j) ? 0.0 : h);
+        }
+        dh_part = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+      }
+#ifdef MSGPU_STENCIL_STAMPS
+      if (dh_part == 1.2345e-300) st_t[7] += 1;  // the stamp below must wait for the SpMV
+#endif
+      MSGPU_STAMP(1)  // SpMV + own part of d.h
+      if (start) {
+        start = false;
+        __syncthreads();  // everybody is done with x in dv
+        stage_in(bk);
+        __syncthreads();
+        double part = 0.0;
+        MSGPU_TILE(c, j) {
+          gg[c][j] = hh[c][j] - dvt[c * P + j];
+          part += gg[c][j] * (shadow(j) ? 0.0 : gg[c][j]);
+        }
+        res = sqrt(block_sum12(part, red));
+        if (res <= a.tol) {
+          ok = true;
+          break;
+        }
+        // the barrier inside block_sum12 separates the reads of b from this overwrite of dv
+        MSGPU_TILE(c, j) dl[c][j] = -gg[c][j];
+        MSGPU_PUBLISH(dl);
+        gh = res * res;
+        rgh = FAST ? 1.0 / gh : 0.0;
+        if (FAST) res = gh;
+        continue;
+      }
+      ++it;
+      const double dh = block_sum12(dh_part, red + ST_RED);
+#ifdef MSGPU_STENCIL_STAMPS
+      if (dh == 1.2345e-300) st_t[7] += 1;
+#endif
+      MSGPU_STAMP(2)  // first reduction
+      const double alpha = gh / dh;
+#ifdef MSGPU_STENCIL_STAMPS
+      if (alpha == 1.2345e-300) st_t[7] += 1;
+#endif
+      MSGPU_STAMP(3)  // alpha
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      MSGPU_TILE(c, j) {
+        xx[c][j] += alpha * dl[c][j];
+        gg[c][j] += alpha * hh[c][j];
+        acc[(c * KR + j) & 3] += gg[c][j] * (shadow(j) ? 0.0 : gg[c][j]);
+      }
+      const double part2 = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#ifdef MSGPU_STENCIL_STAMPS
+      if (part2 == 1.2345e-300) st_t[7] += 1;
+#endif
+      MSGPU_STAMP(4)  // x, g updates + own part of g.g
+      const double s2 = block_sum12(part2, red + 2 * ST_RED);
+#ifdef MSGPU_STENCIL_STAMPS
+      if (s2 == 1.2345e-300) st_t[7] += 1;
+#endif
+      MSGPU_STAMP(5)  // second reduction
+      double gh_new;
+      if (FAST) {
+        res = s2;
+        gh_new = s2;
+        if (s2 <= a.tol2) {
+          ok = true;
+          break;
+        }
+      } else {
+        res = sqrt(s2);
+        gh_new = res * res;
+        if (res <= a.tol) {
+          ok = true;
+          break;
+        }
+      }
+      if (it >= a.max_it || s2 != s2) break;
+      const double beta = FAST ? gh_new * rgh : gh_new / gh;
+      gh = gh_new;
+      if (FAST) rgh = 1.0 / gh;
+      MSGPU_TILE(c, j) dl[c][j] = beta * dl[c][j] - gg[c][j];
+      MSGPU_PUBLISH(dl);
+      MSGPU_STAMP(6)  // beta, new direction, publish
+    }
+    if (FAST && it > 0) res = sqrt(res);
+#ifdef MSGPU_STENCIL_STAMPS
+    st_its += it;
+    for (int i = 0; i < 8; ++i) st_sum[i] += st_t[i];
+#endif
+    // ---- write the solution back: registers -> padded columns -> mesh ordering (coalesced)
+    __syncthreads();
+    MSGPU_PUBLISH(xx);
     __syncthreads();
     for (int c = warp; c < mp; c += nw)
       for (int i = lane; i < mp; i += 32) xk[static_cast<size_t>(c + off) * m + (i + off)] = dv[c * P + i];
@@ -451,9 +365,14 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 2)
     }
     // only nodes of the block were written: the pads of dv are still zero for the next system
   }
-  __syncthreads();
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(s_tmem), "r"(static_cast<uint32_t>(p.alloc)));
+#ifdef MSGPU_STENCIL_STAMPS
+  // debug build: CTA 0 leaves its mean cycles per CG step and phase in res[0..6] (instead of the residual norms)
+  if (blockIdx.x == 0 && tid == 0 && a.res && st_its > 0)
+    for (int i = 0; i < 7; ++i) a.res[i] = static_cast<double>(st_sum[i]) / static_cast<double>(st_its);
+#endif
+#undef MSGPU_STAMP
+#undef MSGPU_PUBLISH
+#undef MSGPU_TILE
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -499,18 +418,26 @@ __global__ void __launch_bounds__(128) k_stencil_compress(MeshDims md, int nsys,
     }
     __syncthreads();
     bool bad = false;
-    if (tid < 3) {
-      // what row5 of the CG kernel relies on (cheap, so checked on every call): in the inner-row class of every
-      // column class up and down couplings coincide, and the couplings to a neighbouring column that exists are
-      // those of the inner class, whose right / left pairs coincide
+    if (tid < STENCIL_TABLE) {
+      // the form the CG kernel relies on (cheap, so checked on every call): vertical couplings depend on the column
+      // class only, horizontal ones on the row class only, the diagonal ones on nothing; a neighbour that does not
+      // exist has a zero entry
+      const int cls = tid / 9, e = tid - 9 * cls, cx = cls / 3, cy = cls - 3 * cx;
+      const bool up = cy < 2, dn = cy > 0, rt = cx < 2, lf = cx > 0;
       const double* in = tab + (1 * 3 + 1) * 9;
-      const double* c = tab + (tid * 3 + 1) * 9;
-      bad |= !(c[1] == c[2]);
-      for (int e = 0; e < 3; ++e) {
-        bad |= !(in[3 + e] == in[6 + e]);
-        if (tid < 2) bad |= !(c[3 + e] == in[3 + e]);
-        if (tid > 0) bad |= !(c[6 + e] == in[6 + e]);
+      double want = tab[tid];
+      switch (e) {
+        case 1: want = up ? tab[(cx * 3 + 1) * 9 + 1] : 0.0; break;
+        case 2: want = dn ? tab[(cx * 3 + 1) * 9 + 1] : 0.0; break;
+        case 3: want = (rt && dn) ? in[3] : 0.0; break;
+        case 4: want = rt ? tab[(1 * 3 + cy) * 9 + 4] : 0.0; break;
+        case 5: want = (rt && up) ? in[5] : 0.0; break;
+        case 6: want = (lf && up) ? in[3] : 0.0; break;
+        case 7: want = lf ? tab[(1 * 3 + cy) * 9 + 4] : 0.0; break;
+        case 8: want = (lf && dn) ? in[5] : 0.0; break;
+        default: break;
       }
+      bad |= !(tab[tid] == want);
     }
     if (verify) {
     for (int rp = tid; rp < mp * mp; rp += 128) {
@@ -538,23 +465,22 @@ __global__ void __launch_bounds__(128) k_stencil_compress(MeshDims md, int nsys,
   }
 }
 
-template <int K>
 int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_sms) {
   const size_t smem = plan_smem_bytes(p);
-  auto kern = k_cg_stencil<K>;
+  auto kern = k_cg_stencil;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
     cudaGetLastError();
     return -1;
   }
-  // CTAs per SM: tensor-memory columns (not known to the occupancy calculator), registers, shared memory
+  // CTAs per SM: registers, shared memory, threads (the kernel is persistent: a CTA that becomes resident late
+  // finds the queue drained)
   cudaFuncAttributes fa{};
   if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) {
     cudaGetLastError();
     return -1;
   }
-  int per_sm = 512 / p.alloc;
-  const int by_regs = 65536 / (fa.numRegs * p.block), by_smem = static_cast<int>((227u * 1024u) / (smem + fa.sharedSizeBytes + 1024));
-  if (per_sm > by_regs) per_sm = by_regs;
+  int per_sm = 65536 / (fa.numRegs * ((p.block + 127) / 128 * 128));  // registers are handed out per 4 warps
+  const int by_smem = static_cast<int>((227u * 1024u) / (smem + fa.sharedSizeBytes + 1024));
   if (per_sm > by_smem) per_sm = by_smem;
   if (per_sm > 2048 / p.block) per_sm = 2048 / p.block;
   if (const char* e = std::getenv("MSGPU_STENCIL_CTAS")) {  // A/B: fewer CTAs per SM than fit
@@ -568,9 +494,9 @@ int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_s
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   if (std::getenv("MSGPU_DEBUG_LAUNCH"))
     std::fprintf(stderr,
-                 "[msgpu] k_cg_stencil<%d>: block %d (S %d, mp %d, pitch %d, overlap %d), %d regs, smem %zu B, TMEM %d cols -> %d "
-                 "CTAs per SM\n",
-                 K, p.block, p.S, p.mp, p.P, p.ov, fa.numRegs, smem, p.alloc, per_sm);
+                 "[msgpu] k_cg_stencil: block %d (%d x %d tiles of %d x %d nodes, mp %d, pitch %d, overlap %d), %d regs, smem "
+                 "%zu B -> %d CTAs per SM\n",
+                 p.block, p.TC, p.S, ST_W, ST_KR, p.mp, p.P, p.ov, fa.numRegs, smem, per_sm);
   long long grid = static_cast<long long>(num_sms) * per_sm;
   if (grid > a.N) grid = a.N;
   kern<<<static_cast<int>(grid), p.block, smem, s>>>(a, p);
@@ -595,14 +521,7 @@ int launch_stencil_compress(cudaStream_t s, const CgArgs& a, int verify) {
 int launch_cg_stencil(cudaStream_t s, const CgArgs& a, int num_sms) {
   StencilPlan p;
   if (!make_plan(a.md, a.dirichlet, p)) return -1;
-  switch (p.K) {
-    case 9: return launch_plan<9>(s, a, p, num_sms);
-    case 10: return launch_plan<10>(s, a, p, num_sms);
-    case 11: return launch_plan<11>(s, a, p, num_sms);
-    case 12: return launch_plan<12>(s, a, p, num_sms);
-    case 13: return launch_plan<13>(s, a, p, num_sms);
-  }
-  return -1;
+  return launch_plan(s, a, p, num_sms);
 }
 
 }  // namespace msgpu
