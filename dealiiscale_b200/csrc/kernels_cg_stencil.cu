@@ -59,6 +59,8 @@ struct StencilPlan {
   int P;      // pitch of a column of d in shared memory (odd, >= mp + 1)
   int ov;     // rows the last strip of a column shares with the strip before it (S*ST_KR - mp)
   int block;  // CTA size
+  int alloc;  // tensor-memory variant: columns a CTA allocates (power of two) ...
+  int cw;     // ... and columns per warp (x, g, h of a tile: 6 * ST_W * ST_KR)
 };
 
 bool make_plan(const MeshDims& md, int dirichlet, StencilPlan& p) {
@@ -72,6 +74,9 @@ bool make_plan(const MeshDims& md, int dirichlet, StencilPlan& p) {
   p.P = (mp + 1) | 1;
   p.ov = p.S * ST_KR - mp;
   p.block = (p.TC * p.S + 31) & ~31;
+  p.cw = 6 * ST_W * ST_KR;
+  p.alloc = 32;
+  while (p.alloc < (p.block / 32 + 3) / 4 * p.cw) p.alloc *= 2;
   return true;
 }
 
@@ -81,6 +86,82 @@ size_t plan_dv_len(const StencilPlan& p) {
   return (static_cast<size_t>(2) + static_cast<size_t>(p.mp + 7) * p.P + 1) & ~static_cast<size_t>(1);
 }
 size_t plan_smem_bytes(const StencilPlan& p) { return (plan_dv_len(p) + 3 * ST_RED + STENCIL_TABLE + 1) * sizeof(double); }
+
+// ------------------------------------------------------------------------------------------------
+// tensor-memory vectors: ND doubles = 2 ND columns of one lane
+template <int ND>
+struct TV {
+  uint32_t r[2 * ND];
+};
+template <int ND>
+__device__ __forceinline__ double tv_get(const TV<ND>& q, int i) {
+  return __hiloint2double(static_cast<int>(q.r[2 * i + 1]), static_cast<int>(q.r[2 * i]));
+}
+
+// Asynchronous loads; tm_wait* takes the destination registers as in/out operands so that no use of them can be
+// scheduled before the wait (tensor memory is not aliased by any pointer: no "memory" clobber needed).
+template <int ND>
+__device__ __forceinline__ void tm_ld(uint32_t a, TV<ND>& q) {
+  if constexpr (ND == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(q.r[0]), "=r"(q.r[1]), "=r"(q.r[2]), "=r"(q.r[3]), "=r"(q.r[4]), "=r"(q.r[5]), "=r"(q.r[6]),
+                   "=r"(q.r[7])
+                 : "r"(a));
+  } else if constexpr (ND == 2) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(q.r[0]), "=r"(q.r[1]), "=r"(q.r[2]), "=r"(q.r[3])
+                 : "r"(a));
+  } else {
+    static_assert(ND == 1, "chunk size");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n" : "=r"(q.r[0]), "=r"(q.r[1]) : "r"(a));
+  }
+}
+template <int ND>
+__device__ __forceinline__ void tm_wait(TV<ND>& q) {
+  if constexpr (ND == 4) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(q.r[0]), "+r"(q.r[1]), "+r"(q.r[2]), "+r"(q.r[3]), "+r"(q.r[4]), "+r"(q.r[5]), "+r"(q.r[6]),
+                   "+r"(q.r[7]));
+  } else if constexpr (ND == 2) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : "+r"(q.r[0]), "+r"(q.r[1]), "+r"(q.r[2]), "+r"(q.r[3]));
+  } else {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : "+r"(q.r[0]), "+r"(q.r[1]));
+  }
+}
+template <int ND>
+__device__ __forceinline__ void tm_wait3(TV<ND>& a, TV<ND>& b, TV<ND>& c) {
+  if constexpr (ND == 4) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(a.r[0]), "+r"(a.r[1]), "+r"(a.r[2]), "+r"(a.r[3]), "+r"(a.r[4]), "+r"(a.r[5]), "+r"(a.r[6]),
+                   "+r"(a.r[7]), "+r"(b.r[0]), "+r"(b.r[1]), "+r"(b.r[2]), "+r"(b.r[3]), "+r"(b.r[4]), "+r"(b.r[5]),
+                   "+r"(b.r[6]), "+r"(b.r[7]), "+r"(c.r[0]), "+r"(c.r[1]), "+r"(c.r[2]), "+r"(c.r[3]), "+r"(c.r[4]),
+                   "+r"(c.r[5]), "+r"(c.r[6]), "+r"(c.r[7]));
+  } else if constexpr (ND == 2) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(a.r[0]), "+r"(a.r[1]), "+r"(a.r[2]), "+r"(a.r[3]), "+r"(b.r[0]), "+r"(b.r[1]), "+r"(b.r[2]),
+                   "+r"(b.r[3]), "+r"(c.r[0]), "+r"(c.r[1]), "+r"(c.r[2]), "+r"(c.r[3]));
+  } else {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(a.r[0]), "+r"(a.r[1]), "+r"(b.r[0]), "+r"(b.r[1]), "+r"(c.r[0]), "+r"(c.r[1]));
+  }
+}
+// Asynchronous store of ONE double (two columns); tm_st_wait before the same thread reads the columns back.  Wider
+// stores want their 4 / 8 source registers consecutive and aligned, which costs more register moves than the extra
+// store instructions do (ncu, round 2: 190 of 680 instructions per CG step were such moves).
+__device__ __forceinline__ void tm_st1(uint32_t a, double v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};\n" ::"r"(a), "r"(__double2loint(v)),
+               "r"(__double2hiint(v)));
+}
+__device__ __forceinline__ void tm_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n"); }
+
+// f(integral_constant<int, ND>, e0) for the chunks [e0, e0 + ND) of E values: fours, then a pair, then one
+template <int E, class F>
+__device__ __forceinline__ void for_each_chunk(F&& f) {
+#pragma unroll
+  for (int c = 0; c < E / 4; ++c) f(std::integral_constant<int, 4>{}, 4 * c);
+  if constexpr ((E % 4) >= 2) f(std::integral_constant<int, 2>{}, E - (E % 4));
+  if constexpr ((E % 2) == 1) f(std::integral_constant<int, 1>{}, E - 1);
+}
 
 // Sum over the CTA, result in every thread: warp partials into `red` (ST_RED slots; the slots of warps the CTA does
 // not have stay zero), one barrier, then every thread adds the first twelve in one fixed tree (bit-reproducible; a
@@ -118,13 +199,19 @@ __device__ __forceinline__ double stencil_row(double cself, double cv, double ch
   return s;
 }
 
-__global__ void __launch_bounds__(ST_MAX_THREADS, 1)
+// TM = false: x, g, h in registers, one CTA of 256 threads per SM.
+// TM = true:  x, g, h in TENSOR MEMORY (6 W KR columns per thread, streamed through registers four values at a time:
+//             tcgen05.ld / tcgen05.st, SASS LDTM / STTM), 128 registers, TWO CTAs per SM: while one system sits in
+//             its reductions and scalar chains the other one keeps the FP64 pipe busy.
+template <bool TM>
+__global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
     k_cg_stencil(const __grid_constant__ CgArgs a, const __grid_constant__ StencilPlan p) {
   if (a.gate != nullptr && ((*a.gate == 0) != (a.gate_run_if_zero != 0))) return;  // the other kernel does the work
   constexpr bool FAST = MSGPU_FAST_SCALARS;
-  constexpr int W = ST_W, KR = ST_KR;
+  constexpr int W = ST_W, KR = ST_KR, E = ST_W * ST_KR;
   extern __shared__ __align__(16) double sm[];
   __shared__ int s_k, s_next;
+  __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
   const int mp = p.mp, P = p.P, m = a.md.m, n = a.md.n, off = p.off, ov = p.ov;
   const int dvlen = (2 + (mp + 7) * P + 1) & ~1;
@@ -143,9 +230,27 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1)
   // rows [0, ov) of a last strip belong to the strip before it: same arithmetic there and here, counted there
   auto shadow = [&](int j) -> bool { return j < KR - 1 && last && j < ov; };
 
+  if (TM && warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     static_cast<uint32_t>(__cvta_generic_to_shared(&s_tmem))),
+                 "r"(static_cast<uint32_t>(p.alloc)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
   for (int i = tid; i < dvlen + 3 * ST_RED + STENCIL_TABLE + 1; i += blockDim.x) sm[i] = 0.0;
+  uint32_t xcol = 0, gcol = 0, hcol = 0;
+  if constexpr (TM) {
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+    // lane quadrant of this warp in bits 31:16, column block of this warp in bits 15:0
+    xcol = s_tmem + ((static_cast<uint32_t>(warp & 3) * 32u) << 16) +
+           static_cast<uint32_t>(warp >> 2) * static_cast<uint32_t>(p.cw);
+    gcol = xcol + 2u * E;
+    hcol = xcol + 4u * E;
+  }
 
   double xx[W][KR], gg[W][KR], dl[W][KR], hh[W][KR];  // solution, residual, search direction, A d: this thread's tile
+                                                      // (TM: only dl; the others live in tensor memory)
   double cself[W][3];  // diagonal entries of the tile's columns: row 0, inner rows, row KR-1 of the tile
   double cvert[W];     // up / down coupling of the tile's columns
   double chor[3];      // left / right coupling for row 0, inner rows, row KR-1 of the tile
@@ -212,9 +317,13 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1)
       cdb = tab[(1 * 3 + 1) * 9 + 5];
     }
     MSGPU_TILE(c, j) {
-      xx[c][j] = dvt[c * P + j];  // idle threads and columns past the mesh read the zero pad
-      dl[c][j] = xx[c][j];
-      gg[c][j] = 0.0;
+      dl[c][j] = dvt[c * P + j];  // idle threads and columns past the mesh read the zero pad
+      if constexpr (TM) {
+        tm_st1(xcol + 2u * (c * KR + j), dl[c][j]);
+      } else {
+        xx[c][j] = dl[c][j];
+        gg[c][j] = 0.0;
+      }
     }
     // The first pass through the loop computes g = A x - b (d = x is in shared memory already), the following
     // ones are CG steps: one place of use for the SpMV.
@@ -264,7 +373,10 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1)
                                  D(c - 1, j - 1), D(c - 1, j), D(c - 1, j + 1), D(c + 1, j - 1), D(c + 1, j),
                                  D(c + 1, j + 1));
           if (c > 0) h = col_live[c] ? h : 0.0;
-          hh[c][j] = h;
+          if constexpr (TM)
+            tm_st1(hcol + 2u * (c * KR + j), h);
+          else
+            hh[c][j] = h;
           acc[(c * KR + j) & 3] += dl[c][j] * (shadow(j) ? 0.0 : h);
         }
         dh_part = (acc[0] + acc[1]) + (acc[2] + acc[3]);
@@ -279,9 +391,28 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1)
         stage_in(bk);
         __syncthreads();
         double part = 0.0;
-        MSGPU_TILE(c, j) {
-          gg[c][j] = hh[c][j] - dvt[c * P + j];
-          part += gg[c][j] * (shadow(j) ? 0.0 : gg[c][j]);
+        if constexpr (TM) {
+          tm_st_wait();
+          for_each_chunk<E>([&](auto nd, int e0) {
+            constexpr int ND = decltype(nd)::value;
+            TV<ND> qh;
+            tm_ld<ND>(hcol + 2u * e0, qh);
+            tm_wait<ND>(qh);
+#pragma unroll
+            for (int i = 0; i < ND; ++i) {
+              const int c = (e0 + i) / KR, j = (e0 + i) % KR;
+              const double go = tv_get<ND>(qh, i) - dvt[c * P + j];
+              part += go * (shadow(j) ? 0.0 : go);
+              tm_st1(gcol + 2u * (e0 + i), go);
+              dl[c][j] = -go;
+            }
+          });
+        } else {
+          MSGPU_TILE(c, j) {
+            gg[c][j] = hh[c][j] - dvt[c * P + j];
+            part += gg[c][j] * (shadow(j) ? 0.0 : gg[c][j]);
+            dl[c][j] = -gg[c][j];
+          }
         }
         res = sqrt(block_sum12(part, red));
         if (res <= a.tol) {
@@ -289,7 +420,6 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1)
           break;
         }
         // the barrier inside block_sum12 separates the reads of b from this overwrite of dv
-        MSGPU_TILE(c, j) dl[c][j] = -gg[c][j];
         MSGPU_PUBLISH(dl);
         gh = res * res;
         rgh = FAST ? 1.0 / gh : 0.0;
@@ -308,10 +438,31 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1)
 #endif
       MSGPU_STAMP(3)  // alpha
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      MSGPU_TILE(c, j) {
-        xx[c][j] += alpha * dl[c][j];
-        gg[c][j] += alpha * hh[c][j];
-        acc[(c * KR + j) & 3] += gg[c][j] * (shadow(j) ? 0.0 : gg[c][j]);
+      if constexpr (TM) {
+        tm_st_wait();  // h of this step (and x, g of the last one) have landed
+        for_each_chunk<E>([&](auto nd, int e0) {
+          constexpr int ND = decltype(nd)::value;
+          TV<ND> qh, qg, qx;
+          tm_ld<ND>(hcol + 2u * e0, qh);
+          tm_ld<ND>(gcol + 2u * e0, qg);
+          tm_ld<ND>(xcol + 2u * e0, qx);
+          tm_wait3<ND>(qh, qg, qx);
+#pragma unroll
+          for (int i = 0; i < ND; ++i) {
+            const int c = (e0 + i) / KR, j = (e0 + i) % KR;
+            const double go = tv_get<ND>(qg, i) + alpha * tv_get<ND>(qh, i);
+            const double xo = tv_get<ND>(qx, i) + alpha * dl[c][j];
+            acc[(e0 + i) & 3] += go * (shadow(j) ? 0.0 : go);
+            tm_st1(gcol + 2u * (e0 + i), go);
+            tm_st1(xcol + 2u * (e0 + i), xo);
+          }
+        });
+      } else {
+        MSGPU_TILE(c, j) {
+          xx[c][j] += alpha * dl[c][j];
+          gg[c][j] += alpha * hh[c][j];
+          acc[(c * KR + j) & 3] += gg[c][j] * (shadow(j) ? 0.0 : gg[c][j]);
+        }
       }
       const double part2 = (acc[0] + acc[1]) + (acc[2] + acc[3]);
 #ifdef MSGPU_STENCIL_STAMPS
@@ -343,8 +494,24 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1)
       const double beta = FAST ? gh_new * rgh : gh_new / gh;
       gh = gh_new;
       if (FAST) rgh = 1.0 / gh;
-      MSGPU_TILE(c, j) dl[c][j] = beta * dl[c][j] - gg[c][j];
-      MSGPU_PUBLISH(dl);
+      if constexpr (TM) {
+        tm_st_wait();
+        for_each_chunk<E>([&](auto nd, int e0) {
+          constexpr int ND = decltype(nd)::value;
+          TV<ND> qg;
+          tm_ld<ND>(gcol + 2u * e0, qg);
+          tm_wait<ND>(qg);
+#pragma unroll
+          for (int i = 0; i < ND; ++i) {
+            const int c = (e0 + i) / KR, j = (e0 + i) % KR;
+            dl[c][j] = beta * dl[c][j] - tv_get<ND>(qg, i);
+            if (col_live[c] && !shadow(j)) dvt[c * P + j] = dl[c][j];
+          }
+        });
+      } else {
+        MSGPU_TILE(c, j) dl[c][j] = beta * dl[c][j] - gg[c][j];
+        MSGPU_PUBLISH(dl);
+      }
       MSGPU_STAMP(6)  // beta, new direction, publish
     }
     if (FAST && it > 0) res = sqrt(res);
@@ -354,7 +521,22 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1)
 #endif
     // ---- write the solution back: registers -> padded columns -> mesh ordering (coalesced)
     __syncthreads();
-    MSGPU_PUBLISH(xx);
+    if constexpr (TM) {
+      tm_st_wait();
+      for_each_chunk<E>([&](auto nd, int e0) {
+        constexpr int ND = decltype(nd)::value;
+        TV<ND> qx;
+        tm_ld<ND>(xcol + 2u * e0, qx);
+        tm_wait<ND>(qx);
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+          const int c = (e0 + i) / KR, j = (e0 + i) % KR;
+          if (col_live[c] && !shadow(j)) dvt[c * P + j] = tv_get<ND>(qx, i);
+        }
+      });
+    } else {
+      MSGPU_PUBLISH(xx);
+    }
     __syncthreads();
     for (int c = warp; c < mp; c += nw)
       for (int i = lane; i < mp; i += 32) xk[static_cast<size_t>(c + off) * m + (i + off)] = dv[c * P + i];
@@ -373,6 +555,12 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1)
 #undef MSGPU_STAMP
 #undef MSGPU_PUBLISH
 #undef MSGPU_TILE
+  if constexpr (TM) {
+    __syncthreads();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(s_tmem),
+                   "r"(static_cast<uint32_t>(p.alloc)));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -465,9 +653,10 @@ __global__ void __launch_bounds__(128) k_stencil_compress(MeshDims md, int nsys,
   }
 }
 
+template <bool TM>
 int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_sms) {
   const size_t smem = plan_smem_bytes(p);
-  auto kern = k_cg_stencil;
+  auto kern = k_cg_stencil<TM>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
     cudaGetLastError();
     return -1;
@@ -483,6 +672,7 @@ int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_s
   const int by_smem = static_cast<int>((227u * 1024u) / (smem + fa.sharedSizeBytes + 1024));
   if (per_sm > by_smem) per_sm = by_smem;
   if (per_sm > 2048 / p.block) per_sm = 2048 / p.block;
+  if (TM && per_sm > 512 / p.alloc) per_sm = 512 / p.alloc;  // tensor-memory columns
   if (const char* e = std::getenv("MSGPU_STENCIL_CTAS")) {  // A/B: fewer CTAs per SM than fit
     const int want = std::atoi(e);
     if (want >= 1 && want < per_sm) per_sm = want;
@@ -494,9 +684,9 @@ int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_s
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   if (std::getenv("MSGPU_DEBUG_LAUNCH"))
     std::fprintf(stderr,
-                 "[msgpu] k_cg_stencil: block %d (%d x %d tiles of %d x %d nodes, mp %d, pitch %d, overlap %d), %d regs, smem "
+                 "[msgpu] k_cg_stencil<%d>: block %d (%d x %d tiles of %d x %d nodes, mp %d, pitch %d, overlap %d), %d regs, smem "
                  "%zu B -> %d CTAs per SM\n",
-                 p.block, p.TC, p.S, ST_W, ST_KR, p.mp, p.P, p.ov, fa.numRegs, smem, per_sm);
+                 TM ? 1 : 0, p.block, p.TC, p.S, ST_W, ST_KR, p.mp, p.P, p.ov, fa.numRegs, smem, per_sm);
   long long grid = static_cast<long long>(num_sms) * per_sm;
   if (grid > a.N) grid = a.N;
   kern<<<static_cast<int>(grid), p.block, smem, s>>>(a, p);
@@ -521,7 +711,9 @@ int launch_stencil_compress(cudaStream_t s, const CgArgs& a, int verify) {
 int launch_cg_stencil(cudaStream_t s, const CgArgs& a, int num_sms) {
   StencilPlan p;
   if (!make_plan(a.md, a.dirichlet, p)) return -1;
-  return launch_plan(s, a, p, num_sms);
+  const char* tm = std::getenv("MSGPU_STENCIL_TMEM");  // "1": vectors in tensor memory, two systems per SM (A/B)
+  if (tm && tm[0] == '1') return launch_plan<true>(s, a, p, num_sms);
+  return launch_plan<false>(s, a, p, num_sms);
 }
 
 }  // namespace msgpu
