@@ -38,6 +38,14 @@ enum ProblemFlags : int {
   PF_PARABOLIC = 2
 };
 
+// Interpreter kernels keep one VM register file per thread in dynamic shared memory (n_regs doubles x threads).
+// vm_prepare_launch opts the kernel in above the 48 KB default and REFUSES programs that need more than an SM has
+// (more than ~220 live temporaries: the launch would fail with "invalid argument"); a refused launcher launches
+// nothing, returns 0, and vm_launch_error() tells why until vm_clear_launch_error().
+bool vm_prepare_launch(const void* kernel, size_t smem_bytes, const char* what);
+const char* vm_launch_error();
+void vm_clear_launch_error();
+
 // K0 tables ---------------------------------------------------------------------------------
 int launch_slots(cudaStream_t s, const VmProgram& prog, const double* xy, int N, double t, double* slots, int n_slots);
 int launch_lines(cudaStream_t s, const VmProgram& prog0, const VmProgram& prog1, const double* coord0,

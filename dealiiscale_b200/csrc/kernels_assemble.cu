@@ -75,9 +75,9 @@ int launch_moments_vec(cudaStream_t s, const VmProgram& progF, const VmProgram& 
   if (MODE == MODE_CONST_F && static_cast<size_t>(progF.n_regs) > regs) regs = progF.n_regs;
   if (regs < 8) regs = 8;
   const size_t smem = regs * TB * sizeof(double);
-  if (smem > 200 * 1024) return -1;
+  if (smem > 200 * 1024) return -1;  // the caller falls back to one VM run per point (W times fewer registers)
   auto kern = k_cell_moments_vec<Q, W, MODE>;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (!vm_prepare_launch(reinterpret_cast<const void*>(kern), smem, "the volume integrand")) return 0;
   kern<<<blocks_for(static_cast<long long>(nk) * md.ncells), TB, smem, s>>>(progF, prog, md, tb, k0, nk, scale, cell,
                                                                             error_flag);
   return 1;
@@ -154,10 +154,34 @@ __global__ void __launch_bounds__(TB) k_mask_dirichlet(MeshDims md, int N, doubl
   body_mask_dirichlet(md, N, diag, static_cast<long long>(blockIdx.x) * TB + threadIdx.x);
 }
 
+thread_local char g_vm_error[256] = {0};
+
 }  // namespace
+
+bool vm_prepare_launch(const void* kernel, size_t smem_bytes, const char* what) {
+  constexpr size_t kLimit = 220 * 1024;
+  if (smem_bytes > kLimit) {
+    std::snprintf(g_vm_error, sizeof g_vm_error,
+                  "%s needs %zu live temporaries per evaluation point; the interpreter kernels hold at most %zu (%zu KB of shared "
+                  "memory per SM)",
+                  what, smem_bytes / (TB * sizeof(double)), kLimit / (TB * sizeof(double)), kLimit / 1024);
+    return false;
+  }
+  if (smem_bytes > 48 * 1024 &&
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)) != cudaSuccess) {
+    cudaGetLastError();
+    std::snprintf(g_vm_error, sizeof g_vm_error, "%s: cannot opt in to %zu bytes of dynamic shared memory", what, smem_bytes);
+    return false;
+  }
+  return true;
+}
+const char* vm_launch_error() { return g_vm_error[0] ? g_vm_error : nullptr; }
+void vm_clear_launch_error() { g_vm_error[0] = 0; }
 
 int launch_slots(cudaStream_t s, const VmProgram& prog, const double* xy, int N, double t, double* slots, int n_slots) {
   if (n_slots == 0 || N == 0) return 0;
+  if (!vm_prepare_launch(reinterpret_cast<const void*>(k_slots), vm_smem(prog, TB), "the per-system part of the expressions"))
+    return 0;
   k_slots<<<blocks_for(N), TB, vm_smem(prog, TB), s>>>(prog, xy, N, t, slots, n_slots);
   return 1;
 }
@@ -169,6 +193,7 @@ int launch_lines(cudaStream_t s, const VmProgram& prog0, const VmProgram& prog1,
   size_t sm = vm_smem(prog0, TB);
   size_t sm1 = vm_smem(prog1, TB);
   if (sm1 > sm) sm = sm1;
+  if (!vm_prepare_launch(reinterpret_cast<const void*>(k_lines), sm, "the per-line part of the expressions")) return 0;
   k_lines<<<blocks_for(static_cast<long long>(N) * P), TB, sm, s>>>(prog0, prog1, coord0, coord1, P, N, slots, n_slots,
                                                                      T0, n0, T1, n1);
   return 1;
@@ -188,6 +213,7 @@ int launch_cell_moments(cudaStream_t s, const MomentPrograms& mp, MeshDims md, T
   // generic quadrature degree (or a program with very many temporaries): one VM run per point
   const VmProgram& prog = mp.has_map ? *mp.full : *mp.G;
   (void)qsum;
+  if (!vm_prepare_launch(reinterpret_cast<const void*>(k_cell_moments), vm_smem(prog, TB), "the volume integrand")) return 0;
   k_cell_moments<<<blocks_for(static_cast<long long>(nk) * md.ncells), TB, vm_smem(prog, TB), s>>>(
       prog, md, tb, qtab, k0, nk, stiffness_scale, mp.has_map, cell, error_flag);
   return 1;
@@ -212,6 +238,7 @@ int upload_constant_tables(int q, const double* qtab, const double* qsum) {
 int launch_face_moments(cudaStream_t s, const VmProgram& prog, int side, MeshDims md, Tables tb, const double* q1d_pt,
                         const double* q1d_wt, int k0, int nk, int has_map, double* face) {
   if (nk == 0) return 0;
+  if (!vm_prepare_launch(reinterpret_cast<const void*>(k_face_moments), vm_smem(prog, TB), "a boundary-face integrand")) return 0;
   k_face_moments<<<blocks_for(static_cast<long long>(nk) * md.nc), TB, vm_smem(prog, TB), s>>>(
       prog, side, md, tb, q1d_pt, q1d_wt, k0, nk, has_map, face);
   return 1;
@@ -222,11 +249,7 @@ int launch_face_moments_all(cudaStream_t s, const VmProgram* const prog[4], Mesh
   if (nk == 0) return 0;
   size_t sm = 0;
   for (int i = 0; i < 4; ++i) sm = vm_smem(*prog[i], TB) > sm ? vm_smem(*prog[i], TB) : sm;
-  if (sm > 48 * 1024) {  // very large programs: one launch per side
-    int n = 0;
-    for (int i = 0; i < 4; ++i) n += launch_face_moments(s, *prog[i], i, md, tb, q1d_pt, q1d_wt, k0, nk, has_map, face);
-    return n;
-  }
+  if (!vm_prepare_launch(reinterpret_cast<const void*>(k_face_moments4), sm, "a boundary-face integrand")) return 0;
   dim3 grid(blocks_for(static_cast<long long>(nk) * md.nc), 4);
   k_face_moments4<<<grid, TB, sm, s>>>(*prog[0], *prog[1], *prog[2], *prog[3], md, tb, q1d_pt, q1d_wt, k0, nk, has_map,
                                         face);
@@ -241,6 +264,7 @@ int launch_gather(cudaStream_t s, const GatherArgs& a) {
 
 int launch_boundary_values(cudaStream_t s, const VmProgram& prog, MeshDims md, Tables tb, int N, double* bv) {
   if (N == 0) return 0;
+  if (!vm_prepare_launch(reinterpret_cast<const void*>(k_boundary_values), vm_smem(prog, TB), "the Dirichlet data")) return 0;
   k_boundary_values<<<blocks_for(static_cast<long long>(N) * 4 * md.nc), TB, vm_smem(prog, TB), s>>>(prog, md, tb, N,
                                                                                                    bv);
   return 1;

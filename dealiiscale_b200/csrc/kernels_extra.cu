@@ -61,6 +61,15 @@ __global__ void __launch_bounds__(TBX) k_reduce_cells(const double* __restrict__
 inline int blocks(long long work) { return static_cast<int>((work + TBX - 1) / TBX); }
 inline size_t smem_for(const VmProgram& p) { return static_cast<size_t>(std::max(8, p.n_regs)) * TBX * sizeof(double); }
 
+#define CKVM()                                                              \
+  do {                                                                      \
+    if (const char* e_ = vm_launch_error()) {                               \
+      ctx->err = e_;                                                        \
+      vm_clear_launch_error();                                              \
+      return MSGPU_ERR_UNSUPPORTED;                                         \
+    }                                                                       \
+  } while (0)
+
 #define CKX(call)                                                           \
   do {                                                                      \
     cudaError_t e_ = (call);                                                \
@@ -83,6 +92,7 @@ int launch_cell_errors(cudaStream_t s, const VmProgram& prog, MeshDims md, const
                        const double* pt, const double* wt, const double* x, int N, double fd, double* cellred,
                        double* out2) {
   const long long work = static_cast<long long>(N) * md.ncells;
+  if (!vm_prepare_launch(reinterpret_cast<const void*>(k_cell_errors), smem_for(prog), "the exact solution")) return 0;
   k_cell_errors<<<blocks(work), TBX, smem_for(prog), s>>>(prog, md, slots, n_slots, qe, pt, wt, x, N, fd, cellred);
   k_reduce_cells<<<blocks(static_cast<long long>(2) * N * 32), TBX, 0, s>>>(cellred, N, md.ncells, out2);
   return 2;
@@ -104,6 +114,7 @@ int launch_cell_residuals(cudaStream_t s, MeshDims md, const double* x, const do
 int launch_cell_point_load(cudaStream_t s, const VmProgram& prog, MeshDims md, const double* slots, int n_slots, int qe,
                            const double* pt, const double* wt, int k0, int nk, double* cell) {
   const long long work = static_cast<long long>(nk) * md.ncells;
+  if (!vm_prepare_launch(reinterpret_cast<const void*>(k_cell_point_load), smem_for(prog), "the projected function")) return 0;
   k_cell_point_load<<<blocks(work), TBX, smem_for(prog), s>>>(prog, md, slots, n_slots, qe, pt, wt, k0, nk, cell);
   return 1;
 }
@@ -161,6 +172,7 @@ int compute_errors(msgpu_ctx* ctx, double* l2, double* h1) {
   else
     ctx->launches += launch_cell_errors(ctx->stream, exact, md, ctx->d_slots, ctx->pp.ps.n_slots(), ctx->eq_degree,
                                         ctx->d_eq_pt, ctx->d_eq_wt, ctx->d_x, N, 1e-8, ctx->d_cellred, ctx->d_err);
+  CKVM();
   CKX(cudaGetLastError());
   std::vector<double> sums(2 * static_cast<size_t>(N));
   CKX(cudaMemcpyAsync(sums.data(), ctx->d_err, sizeof(double) * sums.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -237,6 +249,7 @@ int project_into_solutions(msgpu_ctx* ctx, const VmProgram& prog, int qe, const 
     g.edge = ctx->d_edge;
     ctx->launches += launch_gather(ctx->stream, g);
   }
+  CKVM();
   CKX(cudaMemsetAsync(ctx->d_x, 0, sizeof(double) * N * md.n, ctx->stream));
   CgArgs a{};
   a.md = md;
@@ -380,6 +393,7 @@ int parabolic_assemble(msgpu_ctx* ctx, double dt, double t) {
   r.b = ctx->d_b;
   r.x = ctx->d_x;
   ctx->launches += launch_rhs_and_dirichlet(ctx->stream, r);
+  CKVM();
   CKX(cudaGetLastError());
   return MSGPU_OK;
 }

@@ -35,6 +35,16 @@ namespace {
     }                                                                                         \
   } while (0)
 
+// a launcher refused an interpreter kernel (an expression with more live temporaries than an SM can hold)
+#define CKVM()                                      \
+  do {                                              \
+    if (const char* e_ = vm_launch_error()) {       \
+      ctx->err = e_;                                \
+      vm_clear_launch_error();                      \
+      return MSGPU_ERR_UNSUPPORTED;                 \
+    }                                               \
+  } while (0)
+
 template <typename T>
 int dev_alloc(msgpu_ctx* ctx, T** p, size_t count) {
   if (*p) {
@@ -125,6 +135,7 @@ int build_tables(msgpu_ctx* ctx, double t) {
   ctx->launches += launch_lines(ctx->stream, ps.line0_program(), ps.line1_program(), ctx->d_coord0, ctx->d_coord1,
                                 ctx->md.P, ctx->N, ctx->d_slots, ps.n_slots(), ctx->d_T0, ps.n_line0(), ctx->d_T1,
                                 ps.n_line1());
+  CKVM();
   CK(cudaGetLastError());
   ctx->tables_time = t;
   ctx->tables_valid = 1;
@@ -520,6 +531,7 @@ int msgpu_assemble(msgpu_ctx* ctx) {
     r.x = ctx->d_x;
     ctx->launches += launch_rhs_and_dirichlet(ctx->stream, r);
   }
+  CKVM();
   CK(cudaGetLastError());
   ctx->assembled = 1;
   return MSGPU_OK;

@@ -223,11 +223,104 @@ double orc_ell_time_micro(void* h, const double* u, int k0, int k1, int threads)
     pool.emplace_back([=] {
       for (int k = k0 + t; k < k1; k += threads) {
         m->micro_solver.assemble_one(k);
-        m->micro_solver.solve_one(k);
+        try {
+          m->micro_solver.solve_one(k);
+        } catch (const std::exception&) {
+          // SolverControl::NoConvergence after 1000 steps (the reference would stop here): the time is what is
+          // being measured, the iterate after 1000 steps stays in place
+        }
       }
     });
   for (auto& th : pool) th.join();
   for (int k = k0; k < k1; ++k) (void)m->macro_solver.get_micro_bulk(k);
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// The same micro path with the reference's string-keyed MapMap in the inner loops - "what the original pays"
+// (SURVEY 8d): compute_pullback_objects fills the two std::map<std::string, ...> (micro.cpp:75-94, mapping.cpp:15-27),
+// integrate_cell looks (det_jac, kkt) up per quadrature point and det_jac again per (test function, point)
+// (micro.cpp:108-136), get_micro_bulk once more per point (macro.cpp:134-157); every lookup formats its key with an
+// ostringstream (mapping.cpp:47-57).  One thread, as solve_elliptic runs.  Returns the seconds of assemble + solve +
+// bulk integral for the systems [k0, k1); *build_seconds = the one-off cost of filling the map for them.
+double orc_ell_time_micro_mapmap(void* h, const double* u, int k0, int k1, double* build_seconds) {
+  auto* m = static_cast<elliptic::Manager*>(h);
+  auto& ms = m->micro_solver;
+  std::copy(u, u + ms.num_grids, m->macro_solver.solution.begin());
+  const int p = ms.fem_q_deg, nq = p * p;
+  const double hh = ms.grid.h;
+  MapMap mapmap;
+  auto tb = std::chrono::steady_clock::now();
+  for (int c = 0; c < ms.grid.n_cells(); ++c)
+    for (int k = k0; k < k1; ++k)
+      for (int q = 0; q < nq; ++q) {
+        double y[2];
+        ms.qpoint(c, q, y);
+        const size_t t = ms.table_index(k, c, q);
+        mapmap.set({ms.grid_locations[k][0], ms.grid_locations[k][1]}, {y[0], y[1]}, ms.det_jac[t],
+                   {ms.kkt[3 * t], ms.kkt[3 * t + 1], ms.kkt[3 * t + 2]});
+      }
+  if (build_seconds) *build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count();
+  auto t0 = std::chrono::steady_clock::now();
+  for (int k = k0; k < k1; ++k) {
+    const std::vector<double> px = {ms.grid_locations[k][0], ms.grid_locations[k][1]};
+    std::fill(ms.righthandsides[k].begin(), ms.righthandsides[k].end(), 0.0);
+    std::fill(ms.solutions[k].begin(), ms.solutions[k].end(), 0.0);
+    ms.system_matrices[k].reinit(ms.pattern);
+    for (int c = 0; c < ms.grid.n_cells(); ++c) {
+      double cell_matrix[4][4] = {};
+      double cell_rhs[4] = {};
+      for (int q = 0; q < nq; ++q) {
+        double y[2], dj;
+        std::array<double, 3> kk;
+        ms.qpoint(c, q, y);
+        mapmap.get(px, {y[0], y[1]}, dj, kk);
+        const int qi = q % p, qj = q / p;
+        double g[4][2];
+        q1_grads(ms.qx[qi], ms.qx[qj], g);
+        const double JxW = ms.qw[qi] * ms.qw[qj] * hh * hh;
+        for (int i = 0; i < 4; ++i) {
+          const double gi0 = g[i][0] / hh, gi1 = g[i][1] / hh;
+          const double t0_ = gi0 * kk[0] + gi1 * kk[1], t1_ = gi0 * kk[1] + gi1 * kk[2];
+          for (int j = 0; j < 4; ++j) cell_matrix[i][j] += (t0_ * (g[j][0] / hh) + t1_ * (g[j][1] / hh)) * JxW * dj;
+        }
+      }
+      for (int i = 0; i < 4; ++i)
+        for (int q = 0; q < nq; ++q) {
+          double y[2], mapped[2], v[4], dj;
+          ms.qpoint(c, q, y);
+          mapmap.get_det_jac(px, {y[0], y[1]}, dj);
+          const int qi = q % p, qj = q / p;
+          ms.data.mapping.mmap(ms.grid_locations[k].data(), y, mapped);
+          const double rhs_val = ms.data.micro_rhs.mvalue(ms.grid_locations[k].data(), mapped);
+          q1_values(ms.qx[qi], ms.qx[qj], v);
+          cell_rhs[i] += (u[k] + rhs_val) * v[i] * (ms.qw[qi] * ms.qw[qj] * hh * hh) * dj;
+        }
+      const auto& cd = ms.grid.cell_dofs[c];
+      for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 4; ++j) ms.system_matrices[k].add(cd[i], cd[j], cell_matrix[i][j]);
+        ms.righthandsides[k][cd[i]] += cell_rhs[i];
+      }
+    }
+    std::map<int, double> bv;
+    for (int node = 0; node < ms.grid.n_dofs(); ++node)
+      if (ms.grid.node_on_boundary(node)) {
+        double y[2] = {-1.0 + (node % ms.grid.m) * ms.grid.h, -1.0 + (node / ms.grid.m) * ms.grid.h};
+        bv[ms.grid.node_dof[node]] = ms.data.micro_bc.mvalue(ms.grid_locations[k].data(), y);
+      }
+    apply_boundary_values(bv, ms.system_matrices[k], ms.solutions[k], ms.righthandsides[k]);
+    const CGResult r = solve_cg(ms.system_matrices[k], ms.solutions[k], ms.righthandsides[k], 1000, 1e-12, nullptr);
+    ms.cg_iterations[k] = r.iterations;
+    double integral = 0;
+    for (int c = 0; c < ms.grid.n_cells(); ++c)
+      for (int q = 0; q < nq; ++q) {
+        double y[2], dj;
+        ms.qpoint(c, q, y);
+        mapmap.get_det_jac(px, {y[0], y[1]}, dj);
+        const int qi = q % p, qj = q / p;
+        integral += q1_interp(ms.grid, ms.solutions[k], c, ms.qx[qi], ms.qx[qj]) * dj * (ms.qw[qi] * ms.qw[qj] * hh * hh);
+      }
+    m->macro_solver.micro_contribution[k] = integral;
+  }
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
