@@ -80,6 +80,9 @@ struct msgpu_ctx {
   int eq_degree = 0;
   double parabolic_dt = -1.0;
   int *d_iters = nullptr, *d_flags = nullptr;
+  double* d_cg_ws = nullptr;    // scratch of the streaming CG kernel (grown on demand, this context's device)
+  size_t cg_ws_bytes = 0;
+  msgpu::CgSwitches cg_sw;      // MSGPU_* switches of the CG launchers, read at msgpu_create / msgpu_reload_switches
   double* d_stencil = nullptr;  // [N or 1][STENCIL_TABLE] class tables of class-uniform systems (kernels_cg_stencil.cu)
   int stencil_hint = 0;         // 0 not known yet, 1 verified for the current matrix, 2 known not class-uniform
   size_t bytes_allocated = 0;

@@ -114,6 +114,23 @@ struct RhsArgs {
 int launch_rhs_and_dirichlet(cudaStream_t s, const RhsArgs& a);
 
 // K4 batched CG --------------------------------------------------------------------------------
+// A/B and test switches of the CG launchers, read from the MSGPU_* environment ONCE per context (msgpu_create,
+// msgpu_reload_switches) instead of on every launch.
+struct CgSwitches {
+  int stencil = 1;         // MSGPU_CG_STENCIL=0: never take the class-compressed kernel
+  int stencil_tmem = 1;    // MSGPU_STENCIL_TMEM=0: its all-register variant (one system per SM)
+  int stencil_ctas = 0;    // MSGPU_STENCIL_CTAS=n: at most n CTAs of it per SM
+  int force_global = 0;    // MSGPU_CG_VARIANT=global: the streaming kernel
+  int wide = 0;            // MSGPU_CG_WIDE=1: 1024 threads x 5 rows instead of 512 x 9 (strided kernel)
+  int strided = 0;         // MSGPU_CG_STRIDED=1: strided row ownership
+  int tmem = -1;           // MSGPU_CG_TMEM: 0 = plain strip kernel, 5 = force the 512 x 9 shape
+  int tmem_small = 1;      // MSGPU_CG_TMEM_SMALL=0: plain strip kernel for 1153..2304 rows
+  int cluster = 1;         // MSGPU_CG_CLUSTER=0: stream the matrix instead of the cluster kernel
+  int debug_launch = 0;    // MSGPU_DEBUG_LAUNCH: print launch shapes
+  double ssor_omega = 1.0;  // MSGPU_SSOR_OMEGA in (0, 2)
+};
+CgSwitches cg_switches_from_env();
+
 struct CgArgs {
   MeshDims md;
   int N;
@@ -144,6 +161,11 @@ struct CgArgs {
                                  // 1 verified before (matrix unchanged since): compress only; 2 known not uniform
   int dirichlet = 0;             // 1: boundary rows are eliminated Dirichlet rows (identity rows, zero couplings):
                                  //    the CG runs on the inner (m-2)^2 block, the boundary values stay as they are
+  const CgSwitches* sw = nullptr;       // the context's switches; null: read the environment now
+  // scratch of the streaming kernel k_cg_global (systems that fit neither an SM nor a cluster): owned by the caller's
+  // context, grown on demand on the context's device, freed with it
+  double** workspace = nullptr;
+  size_t* workspace_bytes = nullptr;
 };
 constexpr int STENCIL_TABLE = 81;  // 9 position classes x 9 couplings
 // returns launches; *variant = 0 shared-memory resident, 1 global-memory, 2 strip, 3 tensor memory, 4 cluster,
@@ -155,7 +177,7 @@ int launch_cg(cudaStream_t s, const CgArgs& a, int num_sms, int* variant);
 // launch_cg_stencil: the solve.  Both return the number of kernels launched, < 0 on error.
 bool stencil_supported(const MeshDims& md, int dirichlet);
 int launch_stencil_compress(cudaStream_t s, const CgArgs& a, int verify);
-int launch_cg_stencil(cudaStream_t s, const CgArgs& a, int num_sms);
+int launch_cg_stencil(cudaStream_t s, const CgArgs& a, int num_sms, const CgSwitches& sw);
 
 // K5/K6 coupling integrals --------------------------------------------------------------------
 struct CouplingArgs {

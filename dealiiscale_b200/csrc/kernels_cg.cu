@@ -1311,7 +1311,7 @@ size_t tmem_smem_bytes(const MeshDims& md, int K) {
 }
 
 template <int BT, int K>
-int launch_strip_tmem(cudaStream_t s, const CgArgs& a, int num_sms) {
+int launch_strip_tmem(cudaStream_t s, const CgArgs& a, int num_sms, bool debug) {
   const size_t smem = tmem_smem_bytes(a.md, K);
   auto kern = a.precond == 1 ? k_cg_strip_tmem<BT, K, true> : k_cg_strip_tmem<BT, K, false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -1323,7 +1323,7 @@ int launch_strip_tmem(cudaStream_t s, const CgArgs& a, int num_sms) {
   // settle for a split that holds a single CTA of this size
   if (by_tmem > 1) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   const cudaError_t occ = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem);
-  if (std::getenv("MSGPU_DEBUG_LAUNCH"))
+  if (debug)
     std::fprintf(stderr, "[msgpu] k_cg_strip_tmem<%d,%d>: occupancy query %s -> %d CTAs per SM, TMEM allows %d, smem %zu B\n", BT, K,
                  cudaGetErrorName(occ), per_sm, by_tmem, smem);
   // The calculator answers 1 for the 256 x 9 shape although two CTAs fit (2 x 84.5 KB of shared memory, 2 x 32 K
@@ -1394,10 +1394,30 @@ int launch_resident(cudaStream_t s, const CgArgs& a, int num_sms) {
   return 1;
 }
 
-double* g_workspace = nullptr;
-size_t g_workspace_bytes = 0;
-
 }  // namespace
+
+CgSwitches cg_switches_from_env() {
+  CgSwitches w;
+  auto flag = [](const char* name, char c) {
+    const char* e = std::getenv(name);
+    return e != nullptr && e[0] == c;
+  };
+  w.stencil = flag("MSGPU_CG_STENCIL", '0') ? 0 : 1;
+  w.stencil_tmem = flag("MSGPU_STENCIL_TMEM", '0') ? 0 : 1;
+  if (const char* e = std::getenv("MSGPU_STENCIL_CTAS")) w.stencil_ctas = std::atoi(e);
+  w.force_global = flag("MSGPU_CG_VARIANT", 'g') ? 1 : 0;
+  w.wide = flag("MSGPU_CG_WIDE", '1') ? 1 : 0;
+  w.strided = flag("MSGPU_CG_STRIDED", '1') ? 1 : 0;
+  w.tmem = flag("MSGPU_CG_TMEM", '0') ? 0 : (flag("MSGPU_CG_TMEM", '5') ? 5 : -1);
+  w.tmem_small = flag("MSGPU_CG_TMEM_SMALL", '0') ? 0 : 1;
+  w.cluster = flag("MSGPU_CG_CLUSTER", '0') ? 0 : 1;
+  w.debug_launch = std::getenv("MSGPU_DEBUG_LAUNCH") != nullptr ? 1 : 0;
+  if (const char* e = std::getenv("MSGPU_SSOR_OMEGA")) {
+    const double o = std::atof(e);
+    if (o > 0.0 && o < 2.0) w.ssor_omega = o;
+  }
+  return w;
+}
 
 static double squared_threshold(double tol) {
   if (!(tol > 0.0)) return tol == 0.0 ? 0.0 : -1.0;
@@ -1407,18 +1427,14 @@ static double squared_threshold(double tol) {
   return t;
 }
 
-static int launch_cg_general(cudaStream_t s, const CgArgs& a_in, int num_sms, int* variant) {
+static int launch_cg_general(cudaStream_t s, const CgArgs& a_in, int num_sms, int* variant, const CgSwitches& sw) {
   if (a_in.precond == 2 && !(resident_smem_bytes(a_in.md) <= 227 * 1024 && a_in.md.n <= 512 * 9)) return -2;
   CgArgs a = a_in;
   const int n = a.md.n;
   const bool fits = resident_smem_bytes(a.md) <= 227 * 1024 && n <= 512 * 9;  // 512 x 9 rows is the largest strip shape
-  const char* force = std::getenv("MSGPU_CG_VARIANT");  // "global" forces the streaming kernel (tests)
-  if (fits && !(force && force[0] == 'g')) {
+  if (fits && !sw.force_global) {
     if (variant) *variant = 0;
-    const char* wide = std::getenv("MSGPU_CG_WIDE");  // "1": 1024 threads x 5 rows instead of 512 x 9
-    const char* strided = std::getenv("MSGPU_CG_STRIDED");  // "1": strided row ownership (A/B measurements)
-    const char* tmem = std::getenv("MSGPU_CG_TMEM");  // "0": off, "5": force the 512 x 9 shape
-    // default for the large resident sizes: matrix in tensor memory ("0" = plain strip kernel, A/B); the SSOR
+    // default for the large resident sizes: matrix in tensor memory (tmem == 0: plain strip kernel, A/B); the SSOR
     // sweeps need all five diagonals in shared memory and live in the plain strip kernel
     if (a.precond == 2) {
       if (variant) *variant = 2;
@@ -1429,21 +1445,19 @@ static int launch_cg_general(cudaStream_t s, const CgArgs& a_in, int num_sms, in
       if (n <= 2560) return launch_strip<512, 5>(s, a, num_sms);
       return launch_strip<512, 9>(s, a, num_sms);
     }
-    if (!(tmem && tmem[0] == '0') && !(strided && strided[0] == '1') && n > 2560) {
+    if (sw.tmem != 0 && !sw.strided && n > 2560) {
       if (variant) *variant = 3;
-      if (n <= 256 * 17 && !(tmem && tmem[0] == '5')) return launch_strip_tmem<256, 17>(s, a, num_sms);
-      if (n <= 512 * 9) return launch_strip_tmem<512, 9>(s, a, num_sms);
+      if (n <= 256 * 17 && sw.tmem != 5) return launch_strip_tmem<256, 17>(s, a, num_sms, sw.debug_launch != 0);
+      if (n <= 512 * 9) return launch_strip_tmem<512, 9>(s, a, num_sms, sw.debug_launch != 0);
     }
     // mid sizes (1153..2304 rows, e.g. 41 x 41 nodes): 256 threads x 9 rows allocate 256 TMEM columns, two systems
     // share an SM (3.0 instead of 4.4 ms against the plain strip kernel at 2401 systems of 2025 rows).  Below that
     // the plain strip kernel with 3-4 CTAs per SM is the faster one (measured: 128 x 9 with 128 columns loses 12 %).
-    const char* small = std::getenv("MSGPU_CG_TMEM_SMALL");  // "0": plain strip kernel for these sizes (A/B)
-    if (!(tmem && tmem[0] == '0') && !(small && small[0] == '0') && !(strided && strided[0] == '1') && n > 128 * 9 &&
-        n <= 256 * 9) {
+    if (sw.tmem != 0 && sw.tmem_small && !sw.strided && n > 128 * 9 && n <= 256 * 9) {
       if (variant) *variant = 3;
-      return launch_strip_tmem<256, 9>(s, a, num_sms);
+      return launch_strip_tmem<256, 9>(s, a, num_sms, sw.debug_launch != 0);
     }
-    if (!(strided && strided[0] == '1')) {
+    if (!sw.strided) {
       if (variant) *variant = 2;
       if (n <= 32) return launch_strip<32, 1>(s, a, num_sms);
       if (n <= 128) return launch_strip<128, 1>(s, a, num_sms);
@@ -1457,11 +1471,10 @@ static int launch_cg_general(cudaStream_t s, const CgArgs& a_in, int num_sms, in
     if (n <= 384) return launch_resident<128, 3>(s, a, num_sms);
     if (n <= 1280) return launch_resident<256, 5>(s, a, num_sms);
     if (n <= 2560) return launch_resident<512, 5>(s, a, num_sms);
-    if (wide && wide[0] == '1') return launch_resident<1024, 5>(s, a, num_sms);
+    if (sw.wide) return launch_resident<1024, 5>(s, a, num_sms);
     return launch_resident<512, 9>(s, a, num_sms);
   }
-  const char* nocluster = std::getenv("MSGPU_CG_CLUSTER");  // "0": stream the matrix from L2/HBM instead (A/B)
-  if (!(force && force[0] == 'g') && !(nocluster && nocluster[0] == '0') && n > 2560 && n <= 8 * 256 * 17) {
+  if (!sw.force_global && sw.cluster && n > 2560 && n <= 8 * 256 * 17) {
     const int r = launch_cluster(s, a, num_sms);
     if (r > 0) {
       if (variant) *variant = 4;
@@ -1473,12 +1486,18 @@ static int launch_cg_general(cudaStream_t s, const CgArgs& a_in, int num_sms, in
   int grid = num_sms * 2;
   if (grid > a.N) grid = a.N;
   const size_t need = static_cast<size_t>(grid) * 3 * n * sizeof(double);
-  if (need > g_workspace_bytes) {
-    if (g_workspace) cudaFree(g_workspace);
-    if (cudaMalloc(&g_workspace, need) != cudaSuccess) return -1;
-    g_workspace_bytes = need;
+  if (a.workspace == nullptr || a.workspace_bytes == nullptr) return -1;
+  if (need > *a.workspace_bytes) {
+    if (*a.workspace) {
+      cudaStreamSynchronize(s);  // an earlier launch on this stream may still use the old buffer
+      cudaFree(*a.workspace);
+      *a.workspace = nullptr;
+      *a.workspace_bytes = 0;
+    }
+    if (cudaMalloc(a.workspace, need) != cudaSuccess) return -1;
+    *a.workspace_bytes = need;
   }
-  k_cg_global<BT><<<grid, BT, 0, s>>>(a, g_workspace);
+  k_cg_global<BT><<<grid, BT, 0, s>>>(a, *a.workspace);
   return 1;
 }
 
@@ -1494,15 +1513,16 @@ int launch_cg(cudaStream_t s, const CgArgs& a_in, int num_sms, int* variant) {
   cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
   cudaMemsetAsync(a.fail_flag, 0, sizeof(int), s);
   int launched = 0, stencil_variant = 0;
-  const char* st_env = std::getenv("MSGPU_CG_STENCIL");  // "0": never take the class-compressed kernel (A/B, tests)
-  if (a.stencil_ws != nullptr && a.stencil_bad != nullptr && a.precond == 0 && a.stencil_hint != 2 &&
-      !(st_env && st_env[0] == '0') && stencil_supported(a.md, a.dirichlet)) {
+  const CgSwitches sw = a.sw ? *a.sw : cg_switches_from_env();
+  a.sw = nullptr;  // host pointer: not for the kernels
+  if (a.stencil_ws != nullptr && a.stencil_bad != nullptr && a.precond == 0 && a.stencil_hint != 2 && sw.stencil &&
+      stencil_supported(a.md, a.dirichlet)) {
     cudaMemsetAsync(a.stencil_bad, 0, sizeof(int), s);
     launched += launch_stencil_compress(s, a, a.stencil_hint == 0);
     CgArgs st = a;
     st.gate = a.stencil_bad;
     st.gate_run_if_zero = 1;
-    const int r = launch_cg_stencil(s, st, num_sms);
+    const int r = launch_cg_stencil(s, st, num_sms, sw);
     if (r > 0) {
       launched += r;
       stencil_variant = 5;
@@ -1515,7 +1535,7 @@ int launch_cg(cudaStream_t s, const CgArgs& a_in, int num_sms, int* variant) {
     }
   }
   int general_variant = 0;
-  const int r = launch_cg_general(s, a, num_sms, &general_variant);
+  const int r = launch_cg_general(s, a, num_sms, &general_variant, sw);
   if (r < 0) return r;
   if (variant) *variant = stencil_variant ? (stencil_variant | (general_variant << 8)) : general_variant;
   return launched + r;

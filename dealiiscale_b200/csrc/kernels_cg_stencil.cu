@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(128) k_stencil_compress(MeshDims md, int nsys,
 }
 
 template <bool TM, int W, int KR, bool OV, bool DC>
-int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_sms) {
+int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_sms, const CgSwitches& sw) {
   const size_t smem = plan_smem_bytes(p);
   auto kern = k_cg_stencil<TM, W, KR, OV, DC>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
@@ -716,16 +716,13 @@ int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_s
   if (per_sm > by_smem) per_sm = by_smem;
   if (per_sm > 2048 / p.block) per_sm = 2048 / p.block;
   if (TM && per_sm > 512 / p.alloc) per_sm = 512 / p.alloc;  // tensor-memory columns
-  if (const char* e = std::getenv("MSGPU_STENCIL_CTAS")) {  // A/B: fewer CTAs per SM than fit
-    const int want = std::atoi(e);
-    if (want >= 1 && want < per_sm) per_sm = want;
-  }
+  if (sw.stencil_ctas >= 1 && sw.stencil_ctas < per_sm) per_sm = sw.stencil_ctas;  // A/B: fewer CTAs per SM than fit
   if (per_sm < 1) per_sm = 1;
   // shared-memory carve-out that holds per_sm CTAs (the rest stays L1)
   int carve = static_cast<int>((per_sm * (smem + fa.sharedSizeBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
   if (carve > 100) carve = 100;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-  if (std::getenv("MSGPU_DEBUG_LAUNCH"))
+  if (sw.debug_launch)
     std::fprintf(stderr,
                  "[msgpu] k_cg_stencil<%d>: block %d (%d x %d tiles of %d x %d nodes, mp %d, pitch %d, overlap %d), %d regs, smem "
                  "%zu B -> %d CTAs per SM\n",
@@ -751,17 +748,16 @@ int launch_stencil_compress(cudaStream_t s, const CgArgs& a, int verify) {
   return 1;
 }
 
-int launch_cg_stencil(cudaStream_t s, const CgArgs& a, int num_sms) {
+int launch_cg_stencil(cudaStream_t s, const CgArgs& a, int num_sms, const CgSwitches& sw) {
   StencilPlan p;
   int shape = 0;
   if (!make_plan(a.md, a.dirichlet, p, &shape)) return -1;
-  const char* tm = std::getenv("MSGPU_STENCIL_TMEM");  // "0": vectors in registers, one system per SM (A/B)
-  const bool use_tm = !(tm && tm[0] == '0');
+  const bool use_tm = sw.stencil_tmem != 0;  // 0: vectors in registers, one system per SM (A/B)
   if (shape == 0)
-    return use_tm ? launch_plan<true, 3, 7, false, false>(s, a, p, num_sms)
-                  : launch_plan<false, 3, 7, false, false>(s, a, p, num_sms);
-  return use_tm ? launch_plan<true, 3, 6, true, true>(s, a, p, num_sms)
-                : launch_plan<false, 3, 6, true, true>(s, a, p, num_sms);
+    return use_tm ? launch_plan<true, 3, 7, false, false>(s, a, p, num_sms, sw)
+                  : launch_plan<false, 3, 7, false, false>(s, a, p, num_sms, sw);
+  return use_tm ? launch_plan<true, 3, 6, true, true>(s, a, p, num_sms, sw)
+                : launch_plan<false, 3, 6, true, true>(s, a, p, num_sms, sw);
 }
 
 }  // namespace msgpu

@@ -265,6 +265,9 @@ int project_into_solutions(msgpu_ctx* ctx, const VmProgram& prog, int qe, const 
   a.res = ctx->d_res;
   a.work_counter = ctx->d_flags + FLAG_COUNTER;
   a.fail_flag = ctx->d_flags + FLAG_CGFAIL;
+  a.sw = &ctx->cg_sw;
+  a.workspace = &ctx->d_cg_ws;
+  a.workspace_bytes = &ctx->cg_ws_bytes;
   int variant = 0;
   const int l = launch_cg(ctx->stream, a, ctx->num_sms, &variant);
   if (l < 0) {

@@ -283,6 +283,9 @@ int msgpu_macro_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int adopt, int
   a.res = M.d_res;
   a.work_counter = M.d_flags;
   a.fail_flag = M.d_flags + 1;
+  a.sw = &ctx->cg_sw;
+  a.workspace = &ctx->d_cg_ws;
+  a.workspace_bytes = &ctx->cg_ws_bytes;
   int variant = 0;
   const int launched = launch_cg(ctx->stream, a, ctx->num_sms, &variant);
   if (launched < 0) return fail(ctx, MSGPU_ERR_CUDA, "macro: the CG kernel could not be launched");

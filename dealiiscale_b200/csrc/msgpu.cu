@@ -67,7 +67,7 @@ void free_all(msgpu_ctx* ctx) {
                   ctx->d_q1pt, ctx->d_q1wt,  ctx->d_cell, ctx->d_face, ctx->d_diag,   ctx->d_b0,     ctx->d_jw,
                   ctx->d_edge, ctx->d_bv,    ctx->d_b,   ctx->d_x,    ctx->d_xold,   ctx->d_u,      ctx->d_w,
                   ctx->d_c,    ctx->d_res,   ctx->d_iters, ctx->d_flags, ctx->d_err,  ctx->d_mass,   ctx->d_macro,
-                  ctx->d_lumped, ctx->d_cellred, ctx->d_eq_pt, ctx->d_eq_wt, ctx->d_stencil};
+                  ctx->d_lumped, ctx->d_cellred, ctx->d_eq_pt, ctx->d_eq_wt, ctx->d_stencil, ctx->d_cg_ws};
   for (void* p : ptrs)
     if (p) cudaFree(p);
 }
@@ -190,6 +190,7 @@ int msgpu_create(msgpu_ctx** out, const msgpu_desc* desc) {
     return MSGPU_ERR_CUDA;
   }
   ctx->own_stream = 1;
+  ctx->cg_sw = cg_switches_from_env();
   try {
     ctx->ref_to_internal = reference_numbering(desc->mesh_kind, desc->cells_per_axis);
   } catch (const std::exception&) {
@@ -221,6 +222,12 @@ int msgpu_set_stream(msgpu_ctx* ctx, void* cuda_stream) {
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   ctx->own_stream = 0;
+  return MSGPU_OK;
+}
+
+int msgpu_reload_switches(msgpu_ctx* ctx) {
+  if (!ctx) return MSGPU_ERR_INVALID;
+  ctx->cg_sw = cg_switches_from_env();
   return MSGPU_OK;
 }
 
@@ -359,6 +366,12 @@ int msgpu_setup(msgpu_ctx* ctx) {
   for (int v = 0; v < md.m; ++v) c0[md.nc * md.q + v] = c1[md.nc * md.q + v] = -1.0 + v * md.h;
 
   ctx->bytes_allocated = 0;
+  // buffers that are allocated at first use and sized by N: a set-up with more grids must not inherit them
+  for (double** p : {&ctx->d_cellred, &ctx->d_mass, &ctx->d_lumped})
+    if (*p) {
+      cudaFree(*p);
+      *p = nullptr;
+    }
   const ProgramSet& ps = ctx->pp.ps;
   if ((rc = dev_alloc(ctx, &ctx->d_xy, 2 * static_cast<size_t>(N)))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_slots, static_cast<size_t>(N) * std::max(1, ps.n_slots())))) return rc;
@@ -558,11 +571,10 @@ int msgpu_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int precond, int* it
     a.tol = abs_tol;
     a.max_it = max_it;
     a.precond = precond;
-    a.omega = 1.0;  // PreconditionSSOR's default relaxation; MSGPU_SSOR_OMEGA in (0, 2) overrides
-    if (const char* e = std::getenv("MSGPU_SSOR_OMEGA")) {
-      const double w = std::atof(e);
-      if (w > 0.0 && w < 2.0) a.omega = w;
-    }
+    a.omega = ctx->cg_sw.ssor_omega;  // PreconditionSSOR's default relaxation 1; MSGPU_SSOR_OMEGA in (0, 2) overrides
+    a.sw = &ctx->cg_sw;
+    a.workspace = &ctx->d_cg_ws;
+    a.workspace_bytes = &ctx->cg_ws_bytes;
     a.iters = ctx->d_iters;
     a.res = ctx->d_res;
     a.work_counter = ctx->d_flags + FLAG_COUNTER;

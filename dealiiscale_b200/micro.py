@@ -132,6 +132,10 @@ class MicroSolver:
     def synchronize(self):
         self._check(self.lib.msgpu_synchronize(self.h))
 
+    def reload_switches(self):
+        """Read the MSGPU_* A/B switches from the environment again (they are read once, when the solver is created)."""
+        self._check(self.lib.msgpu_reload_switches(self.h))
+
     # ---- the reference interface ------------------------------------------------------------
     def set_grid_locations(self, xy):
         xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)

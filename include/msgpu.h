@@ -91,6 +91,10 @@ const char* msgpu_last_error(const msgpu_ctx* ctx);
 /* Run on a caller-provided cudaStream_t instead of the context's own stream (NULL = default stream). */
 int msgpu_set_stream(msgpu_ctx* ctx, void* cuda_stream);
 int msgpu_synchronize(msgpu_ctx* ctx);
+/* The MSGPU_* A/B switches of the CG launchers (MSGPU_CG_STENCIL, MSGPU_CG_VARIANT, MSGPU_CG_TMEM, ...) are read from
+ * the environment once, in msgpu_create; this reads them again (tests and A/B scripts that flip a switch on a live
+ * context).  No reference counterpart. */
+int msgpu_reload_switches(msgpu_ctx* ctx);
 
 /* ---- MicroSolver::set_grid_locations (micro.cpp:242-245) --------------------------------
  * xy[N][2]: the macro support points owned by this context (its shard of the macro DoFs). */

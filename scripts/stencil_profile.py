@@ -35,6 +35,7 @@ def main():
             os.environ.pop("MSGPU_STENCIL_CTAS", None)
         else:
             os.environ["MSGPU_STENCIL_CTAS"] = env
+        ms.reload_switches()
         ms.stats(reset=True)
         reps = 3
         for _ in range(reps):

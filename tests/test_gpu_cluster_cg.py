@@ -78,6 +78,7 @@ def test_cluster_and_streaming_kernels_agree():
     for name, env in (("cluster", None), ("global", "global")):
         if env:
             os.environ["MSGPU_CG_VARIANT"] = env
+        ms.reload_switches()  # the switches are read when the solver is created
         try:
             ms.zero_solutions()
             its = ms.solve()

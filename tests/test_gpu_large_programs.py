@@ -60,7 +60,9 @@ def test_a_program_that_does_not_fit_an_sm_is_refused_with_a_message(monkeypatch
     monkeypatch.setenv("MSGPU_JIT", "0")
     data = EllipticData(os.path.join(INPUT, "elliptic_non_linear.prm"))
     ms = MicroSolver(capi.ELLIPTIC, data, 8)
-    ms.set_function(capi.FN_BC, _many_temporaries(300, "y1"), data.constants)
+    # 18 x 18 = 324 shared point-level subexpressions from 18 distinct constants (the VM holds few constants)
+    terms = [f"sin({i + 1}*y0+{j + 1}*y1)" for i in range(18) for j in range(18)]
+    ms.set_function(capi.FN_BC, "(" + "+".join(terms) + ")+1e-30*(" + "*".join(terms) + ")", data.constants)
     ms.set_grid_locations(np.array([[0.1, 0.2]]))
     with pytest.raises(capi.MsgpuError) as err:
         ms.setup()
