@@ -26,6 +26,10 @@ namespace ms {
 class Distributed {
  public:
   int rank = 0, world = 1, local_rank = 0;
+  // MSGPU_RANKS_SHARE_DEVICE=1 (tests on a one-GPU box): every rank uses device 0.  NCCL refuses two ranks on one
+  // device, so there is no communicator: the coupling integrals travel through peer memory (CUDA IPC works between
+  // processes on one device) and the per-grid scalars of the stop test through the host exchange below.
+  bool share_device = false;
   // Ranks that take part in the CURRENT problem (set by the driver before it builds a Manager).  The partition
   // gives rank r the block [r B, min((r+1) B, N)) with B = ceil(N / R); with few macro points and many ranks the
   // last blocks would be empty (N = 9 on 4 ranks: 3 + 3 + 3 + 0), so a coarse level runs on the largest R <= world
@@ -50,12 +54,20 @@ class Distributed {
       d.rank = std::atoi(r);
       d.world = std::atoi(w);
       d.local_rank = l ? std::atoi(l) : d.rank;
+      const char* share = std::getenv("MSGPU_RANKS_SHARE_DEVICE");
+      d.share_device = share && share[0] == '1';
+      if (d.share_device) d.local_rank = 0;
       const char* dir = std::getenv("MSGPU_RENDEZVOUS_DIR");
       const char* port = std::getenv("MASTER_PORT");
+      // default name: unique per launch (the launcher's pid and run id), private to the user
+      const char* run_id = std::getenv("TORCHELASTIC_RUN_ID");
       d.dir_ = dir ? dir
-                   : "/tmp/msgpu-rdzv-" + std::to_string(static_cast<long>(getppid())) + "-" + (port ? port : "0");
+                   : "/tmp/msgpu-rdzv-" + std::to_string(static_cast<long>(getuid())) + "-" +
+                         std::to_string(static_cast<long>(getppid())) + "-" + (port ? port : "0") + "-" +
+                         (run_id ? run_id : "run");
       std::error_code ec;
       std::filesystem::create_directories(d.dir_, ec);
+      std::filesystem::permissions(d.dir_, std::filesystem::perms::owner_all, std::filesystem::perm_options::replace, ec);
     }
     return d;
   }
@@ -82,6 +94,8 @@ class Distributed {
       for (;;) {
         std::error_code ec;
         if (std::filesystem::exists(f, ec) && std::filesystem::file_size(f, ec) == bytes) break;
+        if (std::filesystem::exists(dir_ + "/abort", ec))
+          throw std::runtime_error("another rank failed (see its message); leaving the exchange");
         if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s)
           throw std::runtime_error("rendezvous timed out waiting for rank " + std::to_string(r) + " (" + f + ")");
         std::this_thread::sleep_for(std::chrono::milliseconds(2));
@@ -101,6 +115,11 @@ class Distributed {
     std::vector<unsigned char> all;
     allgather(blob, bytes, all);
     std::copy(all.begin() + bytes * root, all.begin() + bytes * (root + 1), static_cast<unsigned char*>(blob));
+  }
+  // A rank that is about to die tells the others, so that they do not wait for the time-out.
+  void abort_marker() {
+    if (!active()) return;
+    std::ofstream(dir_ + "/abort") << rank;
   }
   void barrier() {
     unsigned char b = 1;

@@ -71,9 +71,10 @@ class MicroSolver {
     Distributed& d = distributed();
     if (d.active()) {  // ncclGetUniqueId on rank 0 -> everybody -> ncclCommInitRank over the ranks in use
       char id[128] = {};
-      if (d.rank == 0 && ranks_ > 1) check(msgpu_comm_unique_id(id));
+      if (d.rank == 0 && ranks_ > 1 && !d.share_device) check(msgpu_comm_unique_id(id));
       d.broadcast(id, sizeof id, 0);
-      if (ranks_ > 1) check(msgpu_comm_init(ctx_, id, d.rank, ranks_, n_total_, k0_));
+      // ranks sharing one device: no NCCL communicator (id = NULL), the peer-memory exchange must follow
+      if (ranks_ > 1) check(msgpu_comm_init(ctx_, d.share_device ? nullptr : id, d.rank, ranks_, n_total_, k0_));
     }
     check(msgpu_setup(ctx_));
     if (d.active() && wants_p2p(d.ranks_in_use())) {
@@ -98,6 +99,7 @@ class MicroSolver {
       bool all_attached = everybody;
       for (int r = 0; r < ranks_; ++r) all_attached = all_attached && all[r] == 1;
       if (ranks_ > 1 && !all_attached) {
+        if (d.share_device) throw std::runtime_error("ranks share a device and CUDA IPC is unavailable: no exchange path");
         check(msgpu_comm_p2p_detach(ctx_));
         if (d.rank == 0) std::fprintf(stderr, "msgpu: peer-memory exchange unavailable, using ncclAllGather\n");
       }
@@ -153,11 +155,33 @@ class MicroSolver {
     if (c1) c1->assign(n_total_, 0.0);
     check(msgpu_coupling(ctx_, c0.data(), c1 ? c1->data() : dummy.data()));
   }
+  // per-grid scalars of all ranks: local[f][num_grids] -> all[f][n_total].  NCCL (msgpu_comm_allgather); ranks that
+  // share a device have no communicator and go through the host exchange
+  void gather_scalars(const double* local, double* all, int fields) {
+    Distributed& d = distributed();
+    if (!(d.active() && d.share_device && ranks_ > 1)) {
+      check(msgpu_comm_allgather(ctx_, local, all, fields));
+      return;
+    }
+    if (ranks_ != d.world) throw std::runtime_error("ranks that share a device must all take part in every level");
+    const int B = (n_total_ + ranks_ - 1) / ranks_;  // block of msgpu_partition
+    std::vector<double> mine(static_cast<size_t>(fields) * B, 0.0);
+    for (int f = 0; f < fields; ++f)
+      std::copy(local + static_cast<size_t>(f) * num_grids_, local + static_cast<size_t>(f + 1) * num_grids_,
+                mine.begin() + static_cast<size_t>(f) * B);
+    std::vector<unsigned char> blob;
+    d.allgather(mine.data(), mine.size() * sizeof(double), blob);
+    const double* got = reinterpret_cast<const double*>(blob.data());
+    for (int r = 0; r < ranks_; ++r)
+      for (int f = 0; f < fields; ++f)
+        for (int i = 0; i < B && r * B + i < n_total_; ++i)
+          all[static_cast<size_t>(f) * n_total_ + r * B + i] = got[(static_cast<size_t>(r) * fields + f) * B + i];
+  }
   // per-grid norms; the aggregation over the macro mesh is done by the caller (micro.cpp:206-214)
   void grid_errors(std::vector<double>& l2, std::vector<double>& h1) {
     std::vector<double> local(2 * static_cast<size_t>(num_grids_)), all(2 * static_cast<size_t>(n_total_));
     check(msgpu_errors(ctx_, local.data(), local.data() + num_grids_));
-    check(msgpu_comm_allgather(ctx_, local.data(), all.data(), 2));  // a copy on one rank
+    gather_scalars(local.data(), all.data(), 2);  // a copy on one rank
     l2.assign(all.begin(), all.begin() + n_total_);
     h1.assign(all.begin() + n_total_, all.end());
   }
@@ -165,7 +189,7 @@ class MicroSolver {
     std::vector<double> local(num_grids_);
     l2.assign(n_total_, 0.0);
     check(msgpu_residuals(ctx_, local.data()));
-    check(msgpu_comm_allgather(ctx_, local.data(), l2.data(), 1));
+    gather_scalars(local.data(), l2.data(), 1);
   }
   void compute_all_errors(const MacroMesh& macro_mesh, int q, double& l2_error, double& h1_error) {
     std::vector<double> l2, h1;

@@ -45,6 +45,7 @@ int main(int argc, char* argv[]) {
                   std::chrono::duration<double>(t1 - wall0).count(), std::chrono::duration<double>(t2 - t1).count(),
                   std::chrono::duration<double>(t3 - t2).count());
   } catch (const std::exception& e) {
+    ms::distributed().abort_marker();  // the other ranks stop waiting for this one
     std::fprintf(stderr, "solve_biomath: %s\n", e.what());
     return 2;
   }

@@ -33,6 +33,7 @@ int main(int argc, char* argv[]) {
     }
     dist.finalize();
   } catch (const std::exception& e) {
+    ms::distributed().abort_marker();  // the other ranks stop waiting for this one
     std::fprintf(stderr, "solve_parabolic: %s\n", e.what());
     return 2;
   }
