@@ -433,11 +433,17 @@ class OracleBio:
         return self.lib.orc_bio_time_micro(self.h, dptr(u), dptr(w), n_sys, threads)
 
 
-def assert_iterations_consistent(oracle, its_gpu, tol=1e-12, window=8, graze=10.0, unknowns=None):
+def assert_iterations_consistent(oracle, its_gpu, tol=1e-12, window=6, graze=10.0, unknowns=None):
     """CG iteration counts must equal the oracle's, except where the oracle's own recursive residual
     is already within a factor `graze` of the stopping threshold at the earlier of the two counts:
     there the last few steps are driven by rounding (different summation orders in the dot products)
-    and the count may differ by up to `window` steps.  Returns the number of such systems."""
+    and the count may differ by up to `window` steps.  Returns the number of such systems.
+
+    window = 6 is what is observed plus one (scripts/literal_scalars_check.py on a B200, round 2: 282 systems of 15
+    parameter sets / sizes, 225 equal counts, 49 that differ, largest difference 5 - on elliptic_non_linear.prm at
+    refinement 5; at most 1 on every bio set and at the 64-cell baseline size).  The literal scalar recurrence
+    (-DMSGPU_FAST_SCALARS=0) gives the same table: the differences come from the order of the dot-product sums, not
+    from beta = |g'|^2 * (1 / |g|^2)."""
     its_o = oracle.iters()
     grazing = 0
     for k, (a, b) in enumerate(zip(its_gpu, its_o)):
