@@ -235,9 +235,13 @@ __device__ __forceinline__ double stencil_row(double cself, double cv, double ch
 // TM = true:  x, g, h in TENSOR MEMORY (6 W KR columns per thread, streamed through registers four values at a time:
 //             tcgen05.ld / tcgen05.st, SASS LDTM / STTM), 128 registers, TWO CTAs per SM: while one system sits in
 //             its reductions and scalar chains the other one keeps the FP64 pipe busy.
-// W x KR: tile of a thread.  OV / DC: the plan may have rows shared between the last two strips of a column / tile
-// columns past the mesh (compiled out where the mesh divides evenly: their masks cost ~110 selects per CG step).
-template <bool TM, int W, int KR, bool OV, bool DC>
+// W x KR: tile of a thread.  OVN / DCN: rows shared between the last two strips of a column / tile columns past the
+// mesh - an exact count (their masks then touch only those rows / columns; 0: none, compiled out) or -1: whatever the
+// plan says (masks on every row / column that could be affected: ~110 selects per CG step).
+// (Measured and dropped: the couplings of the first and last row of a tile read from the class table in shared memory
+// at their place of use instead of sitting in 16 registers: 8.63 against 8.28 ms; all of g loaded from tensor memory
+// at once in the direction update instead of four values at a time: 8.37 against 8.28 ms.)
+template <bool TM, int W, int KR, int OVN, int DCN>
 __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
     k_cg_stencil(const __grid_constant__ CgArgs a, const __grid_constant__ StencilPlan p) {
   if (a.gate != nullptr && ((*a.gate == 0) != (a.gate_run_if_zero != 0))) return;  // the other kernel does the work
@@ -261,9 +265,16 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
   double* const dvt = dv + ix0 * P + (live ? (last ? mp - KR : s * KR) : 0);  // node (0, 0) of the tile
   bool col_live[W];  // tile columns past the mesh compute zeros and write nothing
 #pragma unroll
-  for (int c = 0; c < W; ++c) col_live[c] = live && (!DC || ix0 + c < mp);
+  for (int c = 0; c < W; ++c) col_live[c] = live && (DCN == 0 || ix0 + c < mp);
+  // can tile column c lie past the mesh at all
+  auto maybe_dead = [](int c) -> bool { return DCN < 0 ? c > 0 : c >= W - DCN; };
   // rows [0, ov) of a last strip belong to the strip before it: same arithmetic there and here, counted there
-  auto shadow = [&](int j) -> bool { return OV && j < KR - 1 && last && j < ov; };
+  auto shadow = [&](int j) -> bool {
+    if (OVN == 0) return false;
+    if (OVN > 0) return j < OVN && last;
+    return j < KR - 1 && last && j < ov;
+  };
+  (void)ov;
 
   if (TM && warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
 // rim of the tile: nobody else reads the inner ones
 #define MSGPU_PUBLISH(v) MSGPU_TILE(c, j) if (col_live[c] && !shadow(j)) dvt[c * P + j] = v[c][j]
 // (with strips that share rows the row below / above a tile can be an inner row of the neighbour: publish everything)
-#define MSGPU_RIM(c, j) (OV || (c) == 0 || (c) == W - 1 || (j) == 0 || (j) == KR - 1)
+#define MSGPU_RIM(c, j) (OVN != 0 || (c) == 0 || (c) == W - 1 || (j) == 0 || (j) == KR - 1)
 #define MSGPU_PUBLISH_RIM(v) \
   MSGPU_TILE(c, j) if (MSGPU_RIM(c, j) && col_live[c] && !shadow(j)) dvt[c * P + j] = v[c][j]
 
@@ -345,10 +356,10 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
 #pragma unroll
       for (int c = 0; c < W; ++c) {
         const int ix = ix0 + c, cx = ix == 0 ? 0 : (ix == mp - 1 ? 2 : 1);
-        cself[c][0] = col_live[c] ? tab[(cx * 3 + cy_lo) * 9] : 0.0;
         cself[c][1] = col_live[c] ? tab[(cx * 3 + 1) * 9] : 0.0;
-        cself[c][2] = col_live[c] ? tab[(cx * 3 + cy_hi) * 9] : 0.0;
         cvert[c] = col_live[c] ? tab[(cx * 3 + 1) * 9 + 1] : 0.0;
+        cself[c][0] = col_live[c] ? tab[(cx * 3 + cy_lo) * 9] : 0.0;
+        cself[c][2] = col_live[c] ? tab[(cx * 3 + cy_hi) * 9] : 0.0;
       }
       chor[0] = tab[(1 * 3 + cy_lo) * 9 + 4];
       chor[1] = tab[(1 * 3 + 1) * 9 + 4];
@@ -412,7 +423,7 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
           double h = stencil_row(cself[c][rc], cvert[c], chor[rc], cda, cdb, D(c, j), D(c, j + 1), D(c, j - 1),
                                  D(c - 1, j - 1), D(c - 1, j), D(c - 1, j + 1), D(c + 1, j - 1), D(c + 1, j),
                                  D(c + 1, j + 1));
-          if (DC && c > 0) h = col_live[c] ? h : 0.0;
+          if (maybe_dead(c)) h = col_live[c] ? h : 0.0;
           if constexpr (TM)
             tm_st1(hcol + 2u * (c * KR + j), h);
           else
@@ -696,10 +707,10 @@ __global__ void __launch_bounds__(128) k_stencil_compress(MeshDims md, int nsys,
   }
 }
 
-template <bool TM, int W, int KR, bool OV, bool DC>
+template <bool TM, int W, int KR, int OVN, int DCN>
 int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_sms, const CgSwitches& sw) {
   const size_t smem = plan_smem_bytes(p);
-  auto kern = k_cg_stencil<TM, W, KR, OV, DC>;
+  auto kern = k_cg_stencil<TM, W, KR, OVN, DCN>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
     cudaGetLastError();
     return -1;
@@ -724,9 +735,9 @@ int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_s
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   if (sw.debug_launch)
     std::fprintf(stderr,
-                 "[msgpu] k_cg_stencil<%d>: block %d (%d x %d tiles of %d x %d nodes, mp %d, pitch %d, overlap %d), %d regs, smem "
+                 "[msgpu] k_cg_stencil<TM %d, OVN %d, DCN %d>: block %d (%d x %d tiles of %d x %d nodes, mp %d, pitch %d, overlap %d), %d regs, smem "
                  "%zu B -> %d CTAs per SM\n",
-                 TM ? 1 : 0, p.block, p.TC, p.S, W, KR, p.mp, p.P, p.ov, fa.numRegs, smem, per_sm);
+                 TM ? 1 : 0, OVN, DCN, p.block, p.TC, p.S, W, KR, p.mp, p.P, p.ov, fa.numRegs, smem, per_sm);
   long long grid = static_cast<long long>(num_sms) * per_sm;
   if (grid > a.N) grid = a.N;
   kern<<<static_cast<int>(grid), p.block, smem, s>>>(a, p);
@@ -753,11 +764,12 @@ int launch_cg_stencil(cudaStream_t s, const CgArgs& a, int num_sms, const CgSwit
   int shape = 0;
   if (!make_plan(a.md, a.dirichlet, p, &shape)) return -1;
   const bool use_tm = sw.stencil_tmem != 0;  // 0: vectors in registers, one system per SM (A/B)
+  const int dc = p.TC * p.W - p.mp;
   if (shape == 0)
-    return use_tm ? launch_plan<true, 3, 7, false, false>(s, a, p, num_sms, sw)
-                  : launch_plan<false, 3, 7, false, false>(s, a, p, num_sms, sw);
-  return use_tm ? launch_plan<true, 3, 6, true, true>(s, a, p, num_sms, sw)
-                : launch_plan<false, 3, 6, true, true>(s, a, p, num_sms, sw);
+    return use_tm ? launch_plan<true, 3, 7, 0, 0>(s, a, p, num_sms, sw) : launch_plan<false, 3, 7, 0, 0>(s, a, p, num_sms, sw);
+  // 65 x 65 nodes (64 x 64 cells, Robin / Neumann boundaries): one shared row, one tile column past the mesh
+  if (use_tm && p.ov == 1 && dc == 1 && sw.stencil_variant != 1) return launch_plan<true, 3, 6, 1, 1>(s, a, p, num_sms, sw);
+  return use_tm ? launch_plan<true, 3, 6, -1, -1>(s, a, p, num_sms, sw) : launch_plan<false, 3, 6, -1, -1>(s, a, p, num_sms, sw);
 }
 
 }  // namespace msgpu
