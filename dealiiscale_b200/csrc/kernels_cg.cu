@@ -1406,7 +1406,6 @@ CgSwitches cg_switches_from_env() {
   w.stencil_tmem = flag("MSGPU_STENCIL_TMEM", '0') ? 0 : 1;
   if (const char* e = std::getenv("MSGPU_STENCIL_CTAS")) w.stencil_ctas = std::atoi(e);
   if (const char* e = std::getenv("MSGPU_STENCIL_VARIANT")) w.stencil_variant = std::atoi(e);
-  if (const char* e = std::getenv("MSGPU_STENCIL_VARIANT")) w.stencil_variant = std::atoi(e);
   w.force_global = flag("MSGPU_CG_VARIANT", 'g') ? 1 : 0;
   w.wide = flag("MSGPU_CG_WIDE", '1') ? 1 : 0;
   w.strided = flag("MSGPU_CG_STRIDED", '1') ? 1 : 0;
