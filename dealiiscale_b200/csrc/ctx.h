@@ -27,6 +27,11 @@ struct MacroDevice {
          *d_res = nullptr;
   int *d_ref2int = nullptr, *d_int2ref = nullptr, *d_iters = nullptr, *d_flags = nullptr;
   int source[2] = {0, 1}, has_system[2] = {0, 0}, rhs_given[2] = {0, 0};
+  // PiSolver's load (pi_solver.cpp:76-122): + int phi_i rho_h pi_h, a product of two finite-element functions
+  int product[2] = {0, 0}, nonlinear[2] = {0, 0};
+  double theta[2] = {0, 0};
+  double* d_old = nullptr;          // [fields][n] the field's previous solution (internal ordering)
+  unsigned char* d_dirichlet = nullptr;  // [fields][n] rows whose load is a boundary value
 };
 
 struct PendingTimer {

@@ -4,8 +4,8 @@
 // Replaces MacroSolver::assemble_system + solve of the reference
 //   src/elliptic-elliptic/macro.cpp:57-114   (one field, Dirichlet on the whole boundary)
 //   src/bio-multiscale/macro.cpp:100-202     (fields u and w)
-//   src/elliptic-parabolic/pi_solver.cpp:76-149 (the solve; its right-hand side is a product of
-//                                               two finite-element functions and stays on the host)
+//   src/elliptic-parabolic/pi_solver.cpp:76-149 (the solve, and the part of its load that changes with the micro
+//                                               solutions: int phi_i rho_h pi_h, k_macro_product)
 // The reference re-assembles the macro matrix in every cycle although it never changes, and its
 // right-hand side is AFFINE in the micro contribution c (macro.cpp:78-93: the interpolated
 // contribution enters the load linearly).  The host therefore hands over, once,
@@ -89,12 +89,65 @@ __global__ void __launch_bounds__(128) k_macro_adopt(int fields, int n, const do
   if (i >= k0 && i < k0 + nk) (f == 0 ? u : w)[i - k0] = v;
 }
 
+// PiSolver::assemble_system (pi_solver.cpp:84-101), the term that depends on the micro solutions:
+//   b_i += sum_cells sum_q phi_i(q) rho_q pi_q JxW,   rho_q = sum_a m_a phi_a(q),  pi_q = sum_a g_a phi_a(q),
+// QGauss(2) on square cells of side h, with the nodal values (pi_solver.cpp:62-73, :235-246)
+//   m = micro mass of the grid at that node (the coupling integral), or min(|m|, 1)            if nonlinear,
+//   g = theta * pi_old,                                              or theta * min(|pi|, sqrt|pi|) if nonlinear.
+// Thread per macro node (internal ordering r = ix*m + iy): its <= 4 cells in a fixed order, the 4 points of a cell in
+// a fixed order, no atomics.  Rows that carry a boundary value keep what the host put there.
+__global__ void __launch_bounds__(128) k_macro_product(int n, int m, double h, double theta, int nonlinear,
+                                                        const double* __restrict__ c, const int* __restrict__ int2ref,
+                                                        const double* __restrict__ x_old,
+                                                        const unsigned char* __restrict__ dirichlet,
+                                                        double* __restrict__ b) {
+  const int r = blockIdx.x * 128 + threadIdx.x;
+  if (r >= n || dirichlet[r]) return;
+  const int ix = r / m, iy = r - ix * m, nc = m - 1;
+  const double gp[2] = {0.5 - 0.28867513459481287, 0.5 + 0.28867513459481287};  // Gauss points of QGauss(2) on [0, 1]
+  auto mval = [&](int node) {
+    const double v = c[int2ref[node]];
+    return nonlinear ? fmin(fabs(v), 1.0) : v;
+  };
+  auto gval = [&](int node) {
+    const double v = x_old[node];
+    const double av = fabs(v);
+    return nonlinear ? theta * fmin(av, sqrt(av)) : theta * v;
+  };
+  double sum = 0.0;
+  for (int dy = -1; dy <= 0; ++dy)
+    for (int dx = -1; dx <= 0; ++dx) {
+      const int cx = ix + dx, cy = iy + dy;
+      if (cx < 0 || cy < 0 || cx >= nc || cy >= nc) continue;
+      const int node[4] = {cx * m + cy, (cx + 1) * m + cy, cx * m + cy + 1, (cx + 1) * m + cy + 1};
+      const int mine = (ix - cx) + 2 * (iy - cy);
+      double mm[4], gg[4];
+      for (int a = 0; a < 4; ++a) {
+        mm[a] = mval(node[a]);
+        gg[a] = gval(node[a]);
+      }
+      for (int qj = 0; qj < 2; ++qj)
+        for (int qi = 0; qi < 2; ++qi) {
+          const double xi = gp[qi], eta = gp[qj];
+          const double v[4] = {(1 - xi) * (1 - eta), xi * (1 - eta), (1 - xi) * eta, xi * eta};
+          double rho_q = 0.0, pi_q = 0.0;
+          for (int a = 0; a < 4; ++a) {
+            pi_q += gg[a] * v[a];
+            rho_q += mm[a] * v[a];
+          }
+          sum += v[mine] * (rho_q * pi_q) * (0.25 * h * h);
+        }
+    }
+  b[r] += sum;
+}
+
 }  // namespace
 
 namespace msgpu {
 void macro_release(msgpu_ctx* ctx) {
   MacroDevice& M = ctx->macro;
-  void* ptrs[] = {M.d_diag, M.d_C, M.d_b0, M.d_b, M.d_x, M.d_all, M.d_res, M.d_ref2int, M.d_int2ref, M.d_iters, M.d_flags};
+  void* ptrs[] = {M.d_diag, M.d_C, M.d_b0, M.d_b, M.d_x, M.d_all, M.d_res, M.d_ref2int, M.d_int2ref, M.d_iters, M.d_flags,
+                  M.d_old, M.d_dirichlet};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   M = MacroDevice();
@@ -226,6 +279,31 @@ int msgpu_macro_set_rhs(msgpu_ctx* ctx, int field, const double* b) {
   return MSGPU_OK;
 }
 
+int msgpu_macro_set_product_load(msgpu_ctx* ctx, int field, double theta, int nonlinear, const double* old0,
+                                 const unsigned char* dirichlet) {
+  if (!ctx || !ctx->macro.ready || field < 0 || field >= ctx->macro.fields || !old0 || !dirichlet) return MSGPU_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  MacroDevice& M = ctx->macro;
+  const int n = M.md.n;
+  if (!M.d_old) {
+    CK(cudaMalloc(&M.d_old, sizeof(double) * M.fields * n));
+    CK(cudaMalloc(&M.d_dirichlet, static_cast<size_t>(M.fields) * n));
+  }
+  std::vector<double> v(n);
+  std::vector<unsigned char> d(n);
+  for (int i = 0; i < n; ++i) {
+    v[M.ref2int[i]] = old0[i];
+    d[M.ref2int[i]] = dirichlet[i];
+  }
+  CK(cudaMemcpyAsync(M.d_old + static_cast<size_t>(field) * n, v.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(M.d_dirichlet + static_cast<size_t>(field) * n, d.data(), n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  M.product[field] = 1;
+  M.theta[field] = theta;
+  M.nonlinear[field] = nonlinear != 0;
+  return MSGPU_OK;
+}
+
 int msgpu_macro_set_solution(msgpu_ctx* ctx, int field, const double* x) {
   if (!ctx || !ctx->macro.ready || field < 0 || field >= ctx->macro.fields || !x) return MSGPU_ERR_INVALID;
   MacroDevice& M = ctx->macro;
@@ -268,6 +346,14 @@ int msgpu_macro_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int adopt, int
     ++ctx->launches;
   }
   M.rhs_given[0] = M.rhs_given[1] = 0;
+  for (int f = 0; f < M.fields; ++f)
+    if (M.product[f]) {  // + int phi_i rho_h pi_h from the device-resident micro masses and the previous solution
+      if (!ctx->c_view) return fail(ctx, MSGPU_ERR_INVALID, "macro: msgpu_coupling has not been called yet");
+      k_macro_product<<<(n + 127) / 128, 128, 0, ctx->stream>>>(
+          n, M.md.m, M.md.h, M.theta[f], M.nonlinear[f], M.source[f] == 0 ? ctx->c_view : ctx->c_view + cfield, M.d_int2ref,
+          M.d_old + static_cast<size_t>(f) * n, M.d_dirichlet + static_cast<size_t>(f) * n, M.d_b + static_cast<size_t>(f) * n);
+      ++ctx->launches;
+    }
   CgArgs a;
   a.md = M.md;
   a.N = M.fields;
@@ -290,6 +376,10 @@ int msgpu_macro_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int adopt, int
   const int launched = launch_cg(ctx->stream, a, ctx->num_sms, &variant);
   if (launched < 0) return fail(ctx, MSGPU_ERR_CUDA, "macro: the CG kernel could not be launched");
   ctx->launches += launched;
+  for (int f = 0; f < M.fields; ++f)
+    if (M.product[f])  // old_solution = solution (pi_solver.cpp:259, :264)
+      CK(cudaMemcpyAsync(M.d_old + static_cast<size_t>(f) * n, M.d_x + static_cast<size_t>(f) * n, sizeof(double) * n,
+                         cudaMemcpyDeviceToDevice, ctx->stream));
   if (adopt) {
     k_macro_adopt<<<blocks, 128, 0, ctx->stream>>>(M.fields, n, M.d_x, M.d_ref2int, M.d_all, static_cast<size_t>(n),
                                                    ctx->comm_ready ? ctx->k_offset : 0, ctx->N, ctx->d_u, ctx->d_w);

@@ -230,6 +230,10 @@ class MicroSolver {
                                  C ? C->val.data() : nullptr, b0.data(), x0.data()));
   }
   void macro_set_rhs(int field, const std::vector<double>& b) { check(msgpu_macro_set_rhs(ctx_, field, b.data())); }
+  void macro_set_product_load(int field, double theta, bool nonlinear, const std::vector<double>& old0,
+                              const std::vector<unsigned char>& dirichlet) {
+    check(msgpu_macro_set_product_load(ctx_, field, theta, nonlinear ? 1 : 0, old0.data(), dirichlet.data()));
+  }
   void macro_set_solution(int field, const std::vector<double>& x) { check(msgpu_macro_set_solution(ctx_, field, x.data())); }
   void macro_get_solution(int field, std::vector<double>& x) { check(msgpu_macro_get_solution(ctx_, field, x.data())); }
   std::vector<int> macro_solve(double tol, int max_it, bool adopt) {

@@ -94,7 +94,9 @@ class PiSolver {
             pi_q += macro_contribution[cd[a]] * v[a];
             rho_q += micro_contribution[cd[a]] * v[a];
           }
-          const double functional = rho_q * pi_q + pde_data.macro_rhs.value(ox + h * Q.pt[i], oy + h * Q.pt[j]);
+          // device path: the product of the two finite-element functions is added by k_macro_product (macro.cu)
+          const double functional = (device_product ? 0.0 : rho_q * pi_q) +
+                                    pde_data.macro_rhs.value(ox + h * Q.pt[i], oy + h * Q.pt[j]);
           for (int a = 0; a < 4; ++a) b[a] += v[a] * functional * Q.wt[i] * Q.wt[j] * h * h;
         }
       for (int a = 0; a < 4; ++a) system_rhs[cd[a]] += b[a];
@@ -104,14 +106,24 @@ class PiSolver {
       if (mesh.on_boundary(d)) boundary_values[d] = pde_data.macro_bc.value(mesh.x_of(d), mesh.y_of(d));
     apply_boundary_values(boundary_values, system_matrix, solution, system_rhs);
   }
-  // A * Laplace with Dirichlet elimination is constant; the load (a product of two
-  // finite-element functions, :96-117) is assembled on the host and only the solve runs on the device.
+  // A * Laplace with Dirichlet elimination is constant.  Of the load the host assembles what
+  // depends on t only (macro_rhs and the boundary values, :97, :102-105); the product of the two finite-element
+  // functions rho_h pi_h (:92-97) is evaluated on the device from the device-resident micro masses and the previous
+  // solution.  Every rank solves (MSGPU_MACRO_BROADCAST: rank 0 alone - then the product stays on the host as well).
   void enable_device() {
     assemble_system();
     const std::vector<double> zero(mesh.n, 0.0);
     micro->macro_setup(1, MSGPU_MESH_SUBDIVIDED, h_inv);
     micro->macro_set_system(0, 0, mesh, system_matrix, nullptr, zero, solution);
     on_device = true;
+    const char* host_product = std::getenv("MSGPU_HOST_PRODUCT");  // A/B: keep the product term on the host
+    if (!MicroSolver::macro_broadcast() && !(host_product && host_product[0] == '1')) {
+      std::vector<unsigned char> dirichlet(mesh.n, 0);
+      for (int d = 0; d < mesh.n; ++d) dirichlet[d] = mesh.on_boundary(d) ? 1 : 0;
+      micro->macro_set_product_load(0, pde_data.data.constants.at("theta"), pde_data.data.params.get_bool("nonlinear"),
+                                    old_solution, dirichlet);
+      device_product = true;
+    }
   }
   void solve() {
     if (micro->solves_macro_here()) {
@@ -161,7 +173,7 @@ class PiSolver {
   std::vector<double> system_rhs, macro_contribution;
   MicroSolver* micro = nullptr;
   int count = 0;
-  bool on_device = false;
+  bool on_device = false, device_product = false;
 };
 
 struct StepRecord {

@@ -204,6 +204,13 @@ int msgpu_broadcast_macro(msgpu_ctx* ctx, double* u_all, double* w_all, int root
  *                           msgpu_coupling); x0 = start vector (Dirichlet values in place), may be NULL
  *   msgpu_macro_set_rhs     a host-assembled right-hand side for the NEXT solve only (PiSolver: its
  *                           load is a product of two finite-element functions)
+ *   msgpu_macro_set_product_load  PiSolver::assemble_system (pi_solver.cpp:76-122): from now on every solve of this
+ *                           field adds  int phi_i rho_h pi_h  (QGauss(2); rho_h, pi_h = Q1 interpolants of the
+ *                           micro masses - the first coupling vector - and of theta * the field's previous solution;
+ *                           nonlinear: min(|m|, 1) and theta * min(|pi|, sqrt|pi|), pi_solver.cpp:62-73, :235-246) to
+ *                           the right-hand side the host gave with msgpu_macro_set_rhs (the part that depends on t
+ *                           only), on every row that is not flagged in dirichlet[n]; old0[n] = the previous solution
+ *                           before the first solve (pi_solver.cpp:55: 5); afterwards it follows the solves
  *   msgpu_macro_solve       b = b0 + C c from the device-resident result of the last msgpu_coupling,
  *                           SolverCG as msgpu_solve (warm start), and, if adopt != 0, the solution
  *                           becomes the macro solution of this rank's micro systems (field 0 -> u,
@@ -212,6 +219,8 @@ int msgpu_macro_setup(msgpu_ctx* ctx, int n_fields, int mesh_kind, int cells_per
 int msgpu_macro_set_system(msgpu_ctx* ctx, int field, int source, const int* rowstart, const int* col,
                            const double* A, const double* C, const double* b0, const double* x0);
 int msgpu_macro_set_rhs(msgpu_ctx* ctx, int field, const double* b);
+int msgpu_macro_set_product_load(msgpu_ctx* ctx, int field, double theta, int nonlinear, const double* old0,
+                                 const unsigned char* dirichlet);
 int msgpu_macro_set_solution(msgpu_ctx* ctx, int field, const double* x);
 int msgpu_macro_get_solution(msgpu_ctx* ctx, int field, double* x);
 int msgpu_macro_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int adopt, int* iters);

@@ -201,3 +201,38 @@ def test_device_and_host_macro_paths_agree():
     assert out["device"][0] == out["host"][0]
     for a, b in zip(out["device"][1:], out["host"][1:]):
         assert rel_l2(a, b) < 1e-10
+
+
+@pytest.mark.parametrize("prm", ["linear_time.prm", "full_nonlinear.prm"])
+def test_pi_solver_load_on_the_device_equals_the_host_assembly(prm):
+    """PiSolver::assemble_system (pi_solver.cpp:76-122): the load term  int phi_i rho_h pi_h  - a product of two
+    finite-element functions, with min(|m|, 1) and theta*min(|pi|, sqrt|pi|) in the nonlinear set - is evaluated by
+    k_macro_product on the device from the device-resident micro masses and the previous macro solution;
+    MSGPU_HOST_PRODUCT=1 keeps the reference's host loop.  Same histories, step by step."""
+    lib = _drivers()
+    h_inv, t_inv = 16, 8
+    out = {}
+    for name, env in (("device", None), ("host", "1")):
+        if env:
+            os.environ["MSGPU_HOST_PRODUCT"] = env
+        try:
+            h = C.c_void_p(lib.msdrv_parabolic_create(_path(prm), h_inv, h_inv, t_inv))
+            assert h.value, lib.msdrv_last_error()
+            steps = lib.msdrv_parabolic_run(h, -1)
+            assert steps >= 4, lib.msdrv_last_error()
+            N, n = C.c_int(), C.c_int()
+            lib.msdrv_parabolic_sizes(h, C.byref(N), C.byref(n))
+            N, n = N.value, n.value
+            hist = []
+            for s in range(steps):
+                sc, pi, mass = np.zeros(5), np.zeros(N), np.zeros(N)
+                rho, its = np.zeros((N, n)), np.zeros(N, dtype=np.int32)
+                lib.msdrv_parabolic_history(h, s, dptr(sc), dptr(pi), dptr(mass), dptr(rho), iptr(its))
+                hist.append((pi.copy(), mass.copy(), rho.copy()))
+            out[name] = (lib.msdrv_parabolic_first_step_passes(h), hist)
+            lib.msdrv_parabolic_destroy(h)
+        finally:
+            os.environ.pop("MSGPU_HOST_PRODUCT", None)
+    assert out["device"][0] == out["host"][0] and len(out["device"][1]) == len(out["host"][1])
+    for (pa, ma, ra), (pb, mb, rb) in zip(out["device"][1], out["host"][1]):
+        assert rel_l2(pa, pb) < 1e-11 and rel_l2(ma, mb) < 1e-11 and rel_l2(ra, rb) < 1e-11
