@@ -2,10 +2,13 @@
 #include "jit.h"
 
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -27,6 +30,8 @@ struct Nvrtc {
   int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
   int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  int (*Version)(int*, int*) = nullptr;
+  int version = 0;  // major * 1000 + minor
 };
 
 Nvrtc& nvrtc() {
@@ -54,6 +59,9 @@ Nvrtc& nvrtc() {
     bind(n.GetProgramLogSize, "nvrtcGetProgramLogSize");
     bind(n.GetProgramLog, "nvrtcGetProgramLog");
     bind(n.GetErrorString, "nvrtcGetErrorString");
+    bind(n.Version, "nvrtcVersion");
+    int major = 0, minor = 0;
+    if (ok && n.Version(&major, &minor) == 0) n.version = major * 1000 + minor;
     if (!ok) {
       n.tried = "libnvrtc lacks a required entry point";
       dlclose(n.handle);
@@ -61,6 +69,75 @@ Nvrtc& nvrtc() {
     }
   });
   return n;
+}
+
+// ------------------------------------------------------------------------------ cubins on disk
+// NVRTC needs 0.4 - 2 s per specialised kernel; the cubin depends on nothing but the source text, the NVRTC version
+// and the target, so it is kept in a per-user directory (MSGPU_JIT_CACHE, default $XDG_CACHE_HOME/msgpu or
+// ~/.cache/msgpu, falling back to /tmp/msgpu-jit-<uid>; MSGPU_JIT_CACHE=off disables it) under the hash of exactly
+// that.  Files are written to a temporary name and renamed, so a reader never sees a partial cubin; a file that does
+// not load is ignored and overwritten.
+std::string cache_dir() {
+  const char* e = std::getenv("MSGPU_JIT_CACHE");
+  if (e && (std::strcmp(e, "off") == 0 || std::strcmp(e, "0") == 0)) return "";
+  std::string dir;
+  if (e && e[0]) {
+    dir = e;
+  } else if (const char* x = std::getenv("XDG_CACHE_HOME")) {
+    dir = std::string(x) + "/msgpu";
+  } else if (const char* h = std::getenv("HOME")) {
+    dir = std::string(h) + "/.cache/msgpu";
+    mkdir((std::string(h) + "/.cache").c_str(), 0700);
+  } else {
+    dir = "/tmp/msgpu-jit-" + std::to_string(static_cast<long>(getuid()));
+  }
+  if (mkdir(dir.c_str(), 0700) != 0) {
+    struct stat st {};
+    if (stat(dir.c_str(), &st) != 0 || !S_ISDIR(st.st_mode) || st.st_uid != getuid()) return "";
+  }
+  return dir;
+}
+
+std::string cache_key(const std::string& kernel_name, const std::string& src, int nvrtc_version) {
+  // FNV-1a, 2 x 64 bit (two different offsets), over version, target, name and source
+  unsigned long long h1 = 1469598103934665603ull, h2 = 1099511628211ull * 31 + 7;
+  auto feed = [&](const std::string& t) {
+    for (unsigned char c : t) {
+      h1 = (h1 ^ c) * 1099511628211ull;
+      h2 = (h2 ^ (c + 0x9e)) * 1099511628211ull;
+    }
+  };
+  feed("nvrtc " + std::to_string(nvrtc_version) + " sm_100a c++17 lineinfo\n");
+  feed(kernel_name + "\n");
+  feed(src);
+  char buf[40];
+  std::snprintf(buf, sizeof buf, "%016llx%016llx", h1, h2);
+  return buf;
+}
+
+bool cache_read(const std::string& path, std::vector<char>& cubin) {
+  std::ifstream in(path, std::ios::binary | std::ios::ate);
+  if (!in) return false;
+  const std::streamsize n = in.tellg();
+  if (n < 64) return false;
+  cubin.resize(static_cast<size_t>(n));
+  in.seekg(0);
+  in.read(cubin.data(), n);
+  return static_cast<bool>(in) && std::memcmp(cubin.data(), "\x7f" "ELF", 4) == 0;
+}
+
+void cache_write(const std::string& path, const std::vector<char>& cubin) {
+  const std::string tmp = path + "." + std::to_string(static_cast<long>(getpid())) + ".tmp";
+  {
+    std::ofstream out(tmp, std::ios::binary);
+    if (!out) return;
+    out.write(cubin.data(), static_cast<std::streamsize>(cubin.size()));
+    if (!out) {
+      unlink(tmp.c_str());
+      return;
+    }
+  }
+  if (rename(tmp.c_str(), path.c_str()) != 0) unlink(tmp.c_str());
 }
 
 std::mutex g_cache_mutex;
@@ -93,6 +170,16 @@ int jit_compile(const std::string& src, const char* kernel_name, JitKernel* out,
     *out = hit->second;
     return 0;
   }
+  std::string disk;
+  bool from_disk = false;
+  if (ce.cubin.empty()) {
+    const std::string dir = cache_dir();
+    if (!dir.empty()) {
+      disk = dir + "/" + cache_key(kernel_name, src, n.version) + ".cubin";
+      from_disk = cache_read(disk, ce.cubin);
+      if (!from_disk) ce.cubin.clear();
+    }
+  }
   if (ce.cubin.empty()) {
     nvrtcProgram prog = nullptr;
     int rc = n.CreateProgram(&prog, src.c_str(), "msgpu_jit.cu", 0, nullptr, nullptr);
@@ -121,10 +208,22 @@ int jit_compile(const std::string& src, const char* kernel_name, JitKernel* out,
       if (log) *log = "nvrtcGetCUBIN failed";
       return 1;
     }
+    if (!disk.empty()) cache_write(disk, ce.cubin);
   }
   JitKernel jk;
   cudaError_t e = cudaLibraryLoadData(&jk.lib, ce.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
   if (e == cudaSuccess) e = cudaLibraryGetKernel(&jk.kernel, jk.lib, kernel_name);
+  if (e != cudaSuccess && from_disk) {
+    // a stale or damaged file: forget it and compile (one recursion: the entry is empty again and the file is gone)
+    cudaGetLastError();
+    ce.cubin.clear();
+    unlink(disk.c_str());
+    g_cache.erase(std::string(kernel_name) + "\n" + src);
+    g_cache_mutex.unlock();
+    const int rc = jit_compile(src, kernel_name, out, log);
+    g_cache_mutex.lock();
+    return rc;
+  }
   if (e != cudaSuccess) {
     if (log) *log = std::string("loading the compiled kernel: ") + cudaGetErrorString(e);
     cudaGetLastError();

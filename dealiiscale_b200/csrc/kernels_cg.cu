@@ -81,6 +81,7 @@ __device__ __forceinline__ double block_sum_tree(double v, double* red) {
   return t[0];
 }
 
+#ifdef MSGPU_AB_VARIANTS  // superseded generation, kept for A/B measurements (scripts/cg_variants.py): -DMSGPU_AB_VARIANTS
 // -------------------------------------------------------------------------------------------
 // Shared-memory resident CG.  BT threads, RPT rows per thread (BT*RPT >= n).
 template <int BT, int RPT, bool JACOBI>
@@ -248,6 +249,8 @@ __global__ void __launch_bounds__(BT, 1) k_cg_resident(CgArgs a) {
   }
 }
 
+
+#endif  // MSGPU_AB_VARIANTS
 
 // -------------------------------------------------------------------------------------------
 // Shared-memory resident CG, strip ownership: thread t owns the K consecutive rows t*K .. t*K+K-1
@@ -1380,6 +1383,7 @@ int launch_cluster(cudaStream_t s, const CgArgs& a, int num_sms) {
   return 1;
 }
 
+#ifdef MSGPU_AB_VARIANTS
 template <int BT, int RPT>
 int launch_resident(cudaStream_t s, const CgArgs& a, int num_sms) {
   const size_t smem = resident_smem_bytes(a.md);
@@ -1393,6 +1397,8 @@ int launch_resident(cudaStream_t s, const CgArgs& a, int num_sms) {
   kern<<<static_cast<int>(grid), BT, smem, s>>>(a);
   return 1;
 }
+
+#endif  // MSGPU_AB_VARIANTS
 
 }  // namespace
 
@@ -1446,7 +1452,7 @@ static int launch_cg_general(cudaStream_t s, const CgArgs& a_in, int num_sms, in
       if (n <= 2560) return launch_strip<512, 5>(s, a, num_sms);
       return launch_strip<512, 9>(s, a, num_sms);
     }
-    if (sw.tmem != 0 && !sw.strided && n > 2560) {
+    if (sw.tmem != 0 && n > 2560) {
       if (variant) *variant = 3;
       if (n <= 256 * 17 && sw.tmem != 5) return launch_strip_tmem<256, 17>(s, a, num_sms, sw.debug_launch != 0);
       if (n <= 512 * 9) return launch_strip_tmem<512, 9>(s, a, num_sms, sw.debug_launch != 0);
@@ -1454,26 +1460,28 @@ static int launch_cg_general(cudaStream_t s, const CgArgs& a_in, int num_sms, in
     // mid sizes (1153..2304 rows, e.g. 41 x 41 nodes): 256 threads x 9 rows allocate 256 TMEM columns, two systems
     // share an SM (3.0 instead of 4.4 ms against the plain strip kernel at 2401 systems of 2025 rows).  Below that
     // the plain strip kernel with 3-4 CTAs per SM is the faster one (measured: 128 x 9 with 128 columns loses 12 %).
-    if (sw.tmem != 0 && sw.tmem_small && !sw.strided && n > 128 * 9 && n <= 256 * 9) {
+    if (sw.tmem != 0 && sw.tmem_small && n > 128 * 9 && n <= 256 * 9) {
       if (variant) *variant = 3;
       return launch_strip_tmem<256, 9>(s, a, num_sms, sw.debug_launch != 0);
     }
-    if (!sw.strided) {
-      if (variant) *variant = 2;
-      if (n <= 32) return launch_strip<32, 1>(s, a, num_sms);
-      if (n <= 128) return launch_strip<128, 1>(s, a, num_sms);
-      if (n <= 384) return launch_strip<128, 3>(s, a, num_sms);
-      if (n <= 1280) return launch_strip<256, 5>(s, a, num_sms);
-      if (n <= 2560) return launch_strip<512, 5>(s, a, num_sms);
-      return launch_strip<512, 9>(s, a, num_sms);
+#ifdef MSGPU_AB_VARIANTS
+    if (sw.strided) {  // first generation: strided row ownership, everything in shared memory
+      if (n <= 32) return launch_resident<32, 1>(s, a, num_sms);
+      if (n <= 128) return launch_resident<128, 1>(s, a, num_sms);
+      if (n <= 384) return launch_resident<128, 3>(s, a, num_sms);
+      if (n <= 1280) return launch_resident<256, 5>(s, a, num_sms);
+      if (n <= 2560) return launch_resident<512, 5>(s, a, num_sms);
+      if (sw.wide) return launch_resident<1024, 5>(s, a, num_sms);
+      return launch_resident<512, 9>(s, a, num_sms);
     }
-    if (n <= 32) return launch_resident<32, 1>(s, a, num_sms);
-    if (n <= 128) return launch_resident<128, 1>(s, a, num_sms);
-    if (n <= 384) return launch_resident<128, 3>(s, a, num_sms);
-    if (n <= 1280) return launch_resident<256, 5>(s, a, num_sms);
-    if (n <= 2560) return launch_resident<512, 5>(s, a, num_sms);
-    if (sw.wide) return launch_resident<1024, 5>(s, a, num_sms);
-    return launch_resident<512, 9>(s, a, num_sms);
+#endif
+    if (variant) *variant = 2;
+    if (n <= 32) return launch_strip<32, 1>(s, a, num_sms);
+    if (n <= 128) return launch_strip<128, 1>(s, a, num_sms);
+    if (n <= 384) return launch_strip<128, 3>(s, a, num_sms);
+    if (n <= 1280) return launch_strip<256, 5>(s, a, num_sms);
+    if (n <= 2560) return launch_strip<512, 5>(s, a, num_sms);
+    return launch_strip<512, 9>(s, a, num_sms);
   }
   if (!sw.force_global && sw.cluster && n > 2560 && n <= 8 * 256 * 17) {
     const int r = launch_cluster(s, a, num_sms);
