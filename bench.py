@@ -497,6 +497,7 @@ def main():
 
     from dealiiscale_b200 import capi
     from dealiiscale_b200.micro import MicroSolver, unique_id
+    from dealiiscale_b200.parallel import MacroSharding
     from dealiiscale_b200.prm import BioData
 
     n_gpus = world
@@ -505,7 +506,8 @@ def main():
     data = BioData(prm_path)
     xy_all = macro_points(macro_cells, n_gpus, strong=args.scaling == "strong")
     n_total = xy_all.shape[0]
-    k0, k1 = capi.partition(n_total, n_gpus, rank)
+    sharding = MacroSharding(n_total, rank, n_gpus)  # contiguous blocks of macro points, as msgpu_partition
+    k0, k1 = sharding.k0, sharding.k1
     u_all, w_all = macro_values(xy_all)
 
     ms = MicroSolver(capi.BIO, data, micro_cells, device=local_rank)
@@ -619,14 +621,10 @@ def main():
     # ---- exchange check (N > 1): what this rank received for EVERY macro point against what the owner computed --------
     exchange_check = None
     if distributed:
-        mine = torch.zeros(2, n_total, dtype=torch.float64, device="cuda")
-        mine[0, k0:k1] = torch.from_numpy(cu[k0:k1].copy()).cuda()
-        mine[1, k0:k1] = torch.from_numpy(cw[k0:k1].copy()).cuda()
-        dist.all_reduce(mine)  # every entry has exactly one owner: the sum is the owners' values, through torch's NCCL
-        got = torch.from_numpy(np.stack([cu, cw])).cuda()
-        bad = torch.tensor([int((mine != got).sum().item())], dtype=torch.int64, device="cuda")
-        dist.all_reduce(bad)
-        exchange_check = "ok" if int(bad.item()) == 0 else f"{int(bad.item())} entries differ"
+        # an independent allgather of the owners' values through torch.distributed (NCCL) against what libmsgpu's
+        # exchange (fused peer-memory kernel or ncclAllGather) delivered to this rank
+        bad = sharding.check_exchange(cu, cw, local=(cu[k0:k1], cw[k0:k1]), device="cuda")
+        exchange_check = "ok" if bad == 0 else f"{bad} entries differ"
 
     # device-side durations (CUDA events on the launching stream, recorded inside libmsgpu)
     dev_ms_step = (st["ms_tables"] + st["ms_moments"] + st["ms_gather"] + st["ms_cg"] + st["ms_coupling"]) / args.steps

@@ -108,3 +108,33 @@ def test_coarse_levels_use_only_as_many_ranks_as_have_macro_points():
             assert 1 <= r <= w and all(k1 > k0 for k0, k1 in blocks) and blocks[-1][1] == n
             if r < w:  # one more rank would leave somebody without work
                 assert any(k1 <= k0 for k0, k1 in (partition(n, r + 1, k) for k in range(r + 1)))
+
+
+def _check_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 11  # odd: the last block is padded
+    sh = MacroSharding(n, rank, world)
+    truth = [np.arange(n) * 1.5 + 0.25, -np.arange(n) ** 2 * 1.0]
+    good = sh.check_exchange(*truth, local=[sh.local(t) for t in truth])
+    broken = [t.copy() for t in truth]
+    if rank == 1:
+        broken[1][3] += 1e-9  # one value delivered wrong to one rank
+    bad = sh.check_exchange(*broken, local=[sh.local(t) for t in truth])
+    if rank == 0:
+        np.save(out, np.array([good, bad]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_check_counts_wrong_deliveries(tmp_path):
+    """bench.py's `exchange_check` (MacroSharding.check_exchange): what every rank holds after the exchange against
+    an independent allgather of the owners' values."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = os.path.join(tmp_path, "check.npy")
+    mp.spawn(_check_worker, args=(2, port, out), nprocs=2, join=True)
+    good, bad = np.load(out)
+    assert good == 0 and bad == 1
