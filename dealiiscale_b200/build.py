@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(BUILD, "libmsgpu.so")
 
-CUDA_SOURCES = ["msgpu.cu", "kernels_assemble.cu", "kernels_cg.cu", "kernels_cg_stencil.cu", "kernels_extra.cu", "comm.cu", "macro.cu"]
+CUDA_SOURCES = ["msgpu.cu", "kernels_assemble.cu", "kernels_cg.cu", "kernels_cg_stencil.cu", "kernels_extra.cu", "kernels_norms.cu", "comm.cu", "macro.cu"]
 HOST_SOURCES = ["expr_compile.cpp", "problem_programs.cpp", "jit.cpp", "jit_codegen.cpp"]
 
 NVCC_FLAGS = [

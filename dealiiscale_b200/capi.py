@@ -28,7 +28,8 @@ EXPORTED = [
     "msgpu_get_stats", "msgpu_jit_log", "msgpu_macro_setup", "msgpu_macro_set_system", "msgpu_macro_set_rhs",
     "msgpu_macro_set_solution", "msgpu_macro_get_solution", "msgpu_macro_solve", "msgpu_comm_p2p_export",
     "msgpu_comm_p2p_attach", "msgpu_set_exact_solution", "msgpu_comm_allgather", "msgpu_comm_p2p_detach",
-    "msgpu_reload_switches", "msgpu_macro_set_product_load",
+    "msgpu_reload_switches", "msgpu_macro_set_product_load", "msgpu_norm_setup", "msgpu_norm_of_values",
+    "msgpu_norm_of_residuals", "msgpu_norm_of_errors",
 ]
 
 

@@ -284,6 +284,35 @@ int msgpu_comm_p2p_attach(msgpu_ctx* ctx, const unsigned char* handles) {
 // Per-grid scalars of all ranks (error / residual norms for the stop test):
 // local[fields][N of this rank] -> all[fields][n_total] on every rank.  Host buffers, staged through the
 // padded gather scratch; one grouped ncclAllGather.  Without a communicator it is a copy.
+}  // extern "C"
+
+namespace msgpu {
+// In-place allgather of this rank's block(s) of d_macro (layout [fields][padded]); device buffers only.
+int comm_allgather_macro_buffer(msgpu_ctx* ctx, int fields) {
+  ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm);
+  if (!comm) {
+    ctx->err = "no NCCL communicator";
+    return MSGPU_ERR_COMM;
+  }
+  const int B = comm_block(ctx);
+  const size_t padded = static_cast<size_t>(B) * ctx->n_ranks;
+  const NcclApi& nc = nccl_api();
+  ncclResult_t r = nc.GroupStart();
+  if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclGroupStart");
+  for (int f = 0; f < fields; ++f) {
+    double* base = ctx->d_macro + f * padded;
+    r = nc.AllGather(base + static_cast<size_t>(ctx->rank) * B, base, B, ncclDouble, comm, ctx->stream);
+    if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclAllGather");
+  }
+  r = nc.GroupEnd();
+  if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclGroupEnd");
+  ctx->launches += 1;
+  return MSGPU_OK;
+}
+}  // namespace msgpu
+
+extern "C" {
+
 int msgpu_comm_allgather(msgpu_ctx* ctx, const double* local, double* all, int fields) {
   if (!ctx || !local || !all || fields < 1 || fields > 2) return MSGPU_ERR_INVALID;
   if (!ctx->comm_ready || ctx->n_ranks == 1) {

@@ -34,12 +34,21 @@ struct MacroDevice {
   unsigned char* d_dirichlet = nullptr;  // [fields][n] rows whose load is a boundary value
 };
 
+// The stop test on the device (kernels_norms.cu): the macro mesh in the caller's cell order and scratch.
+struct NormDevice {
+  int ready = 0, n_cells = 0, n_values = 0, q = 0;
+  double h = 0.0;
+  int4* d_cells = nullptr;
+  double *d_values = nullptr, *d_cell_sq = nullptr, *d_out = nullptr, *d_pt = nullptr, *d_wt = nullptr;
+};
+
 struct PendingTimer {
   int phase;
   cudaEvent_t a, b;
 };
 
 void macro_release(msgpu_ctx* ctx);
+void norms_release(msgpu_ctx* ctx);
 
 }  // namespace msgpu
 
@@ -107,6 +116,7 @@ struct msgpu_ctx {
 
   // macro system(s) on the device
   msgpu::MacroDevice macro;
+  msgpu::NormDevice norms;
 
   // multi-GPU
   int comm_ready = 0, rank = 0, n_ranks = 1, n_total = 0, k_offset = 0;

@@ -136,7 +136,8 @@ static int error_quadrature(msgpu_ctx* ctx) {
   return MSGPU_OK;
 }
 
-int compute_errors(msgpu_ctx* ctx, double* l2, double* h1) {
+// d_err[2k], d_err[2k+1] = the per-grid sums of squares (L2 and H1-seminorm parts); no copy to the host
+int launch_grid_error_sums(msgpu_ctx* ctx) {
   if (ctx->pp.prog_err < 0) {
     ctx->err = "no exact solution was set (msgpu_set_function(MSGPU_FN_SOLUTION, ...))";
     return MSGPU_ERR_INVALID;
@@ -174,6 +175,13 @@ int compute_errors(msgpu_ctx* ctx, double* l2, double* h1) {
                                         ctx->d_eq_pt, ctx->d_eq_wt, ctx->d_x, N, 1e-8, ctx->d_cellred, ctx->d_err);
   CKVM();
   CKX(cudaGetLastError());
+  return MSGPU_OK;
+}
+
+int compute_errors(msgpu_ctx* ctx, double* l2, double* h1) {
+  const int rc0 = launch_grid_error_sums(ctx);
+  if (rc0) return rc0;
+  const int N = ctx->N;
   std::vector<double> sums(2 * static_cast<size_t>(N));
   CKX(cudaMemcpyAsync(sums.data(), ctx->d_err, sizeof(double) * sums.size(), cudaMemcpyDeviceToHost, ctx->stream));
   CKX(cudaStreamSynchronize(ctx->stream));
@@ -185,7 +193,8 @@ int compute_errors(msgpu_ctx* ctx, double* l2, double* h1) {
   return MSGPU_OK;
 }
 
-int compute_residuals(msgpu_ctx* ctx, double* l2) {
+// d_err[2k] = ||x_k - x_k_old||^2 per grid; no copy to the host
+int launch_grid_residual_sums(msgpu_ctx* ctx) {
   if (!ctx->d_xold) {
     ctx->err = "residuals are defined for the bio and parabolic problems";
     return MSGPU_ERR_INVALID;
@@ -197,6 +206,13 @@ int compute_residuals(msgpu_ctx* ctx, double* l2) {
   if ((rc = ensure(ctx, &ctx->d_cellred, static_cast<size_t>(N) * 2 * md.ncells))) return rc;
   ctx->launches += launch_cell_residuals(ctx->stream, md, ctx->d_x, ctx->d_xold, N, ctx->d_cellred, ctx->d_err);
   CKX(cudaGetLastError());
+  return MSGPU_OK;
+}
+
+int compute_residuals(msgpu_ctx* ctx, double* l2) {
+  const int rc0 = launch_grid_residual_sums(ctx);
+  if (rc0) return rc0;
+  const int N = ctx->N;
   std::vector<double> sums(2 * static_cast<size_t>(N));
   CKX(cudaMemcpyAsync(sums.data(), ctx->d_err, sizeof(double) * sums.size(), cudaMemcpyDeviceToHost, ctx->stream));
   CKX(cudaStreamSynchronize(ctx->stream));

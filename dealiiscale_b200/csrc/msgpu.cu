@@ -209,6 +209,7 @@ void msgpu_destroy(msgpu_ctx* ctx) {
   drain_timers(ctx);
   comm_destroy(ctx);
   macro_release(ctx);
+  norms_release(ctx);
   free_all(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

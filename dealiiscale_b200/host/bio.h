@@ -166,7 +166,7 @@ class MacroSolver {
   void compute_residual(double& l2_residual) const {  // macro.cpp:230-245: the u part is overwritten by the w part
     std::vector<double> e(mesh.n);
     for (int i = 0; i < mesh.n; ++i) e[i] = sol_w[i] - old_sol_w[i];
-    l2_residual = nodal_l2_norm(mesh, e, 8);
+    l2_residual = (micro && micro->norms_on_device()) ? micro->norm_of_values(e, 8) : nodal_l2_norm(mesh, e, 8);
   }
 
   MacroMesh mesh;
@@ -222,6 +222,7 @@ class Manager {
     micro_solver.set_macro_solution(&macro_solver.sol_u, &macro_solver.sol_w);
     macro_solver.set_micro_objects(&micro_solver);
     if (device_macro_enabled()) macro_solver.enable_device();
+    if (device_macro_enabled()) micro_solver.norm_setup(macro_solver.mesh);  // the stop test on the device as well
     cycle = 0;
     old_residual = 0;
     residual = 1;

@@ -153,6 +153,7 @@ class Manager {
     micro_solver.set_macro_solution(&macro_solver.solution);
     macro_solver.set_micro_objects(&micro_solver);
     if (device_macro_enabled()) macro_solver.enable_device();
+    if (device_macro_enabled()) micro_solver.norm_setup(macro_solver.mesh);  // the stop test on the device as well
     cycle = 0;
   }
   void run() {  // manager.cpp:37-51

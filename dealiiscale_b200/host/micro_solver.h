@@ -191,13 +191,37 @@ class MicroSolver {
     check(msgpu_residuals(ctx_, local.data()));
     gather_scalars(local.data(), l2.data(), 1);
   }
+  // ---- the stop test on the device (include/msgpu.h, msgpu_norm_*): the per-grid norms never reach the host.
+  // Off with MSGPU_HOST_STOP_TEST=1 (A/B) and for ranks that share a device (no NCCL communicator).
+  void norm_setup(const MacroMesh& macro_mesh) {
+    const char* host = std::getenv("MSGPU_HOST_STOP_TEST");
+    Distributed& d = distributed();
+    if ((host && host[0] == '1') || (d.active() && d.share_device)) return;
+    check(msgpu_norm_setup(ctx_, &macro_mesh.cell_dofs[0][0], static_cast<int>(macro_mesh.cell_dofs.size()), macro_mesh.n,
+                           macro_mesh.h));
+    norms_on_device_ = true;
+  }
+  bool norms_on_device() const { return norms_on_device_; }
+  double norm_of_values(const std::vector<double>& v, int q) {
+    double out = 0;
+    check(msgpu_norm_of_values(ctx_, v.data(), q, &out));
+    return out;
+  }
   void compute_all_errors(const MacroMesh& macro_mesh, int q, double& l2_error, double& h1_error) {
+    if (norms_on_device_) {
+      check(msgpu_norm_of_errors(ctx_, q, &l2_error, &h1_error));
+      return;
+    }
     std::vector<double> l2, h1;
     grid_errors(l2, h1);
     l2_error = nodal_l2_norm(macro_mesh, l2, q);
     h1_error = nodal_l2_norm(macro_mesh, h1, q);
   }
   void compute_all_residuals(const MacroMesh& macro_mesh, int q, double& l2_residual) {
+    if (norms_on_device_) {
+      check(msgpu_norm_of_residuals(ctx_, q, &l2_residual));
+      return;
+    }
     std::vector<double> r;
     grid_residuals(r);
     l2_residual = nodal_l2_norm(macro_mesh, r, q);
@@ -261,6 +285,7 @@ class MicroSolver {
   int problem_, cells_, n_dofs_ = 0, num_grids_ = 0, macro_fields_ = 0;
   int n_total_ = 0, k0_ = 0, k1_ = 0;  // all grids / this rank's block
   int ranks_ = 1;                      // ranks sharing this problem
+  bool norms_on_device_ = false;
   const std::vector<double>*macro_u_ = nullptr, *macro_w_ = nullptr;
   void push_macro() {
     if (!macro_u_) throw std::runtime_error("set_macro_solution was not called");

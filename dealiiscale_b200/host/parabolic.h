@@ -212,6 +212,7 @@ class TimeManager {
     rho_solver.set_macro_solution(&pi_solver.solution);
     pi_solver.set_micro_solutions(&rho_solver);
     if (device_macro_enabled()) pi_solver.enable_device();
+    if (device_macro_enabled()) rho_solver.norm_setup(pi_solver.mesh);  // the stop test on the device as well
     it = 0;
   }
   void run() {  // time_manager.cpp:41-62

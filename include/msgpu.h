@@ -225,6 +225,24 @@ int msgpu_macro_set_solution(msgpu_ctx* ctx, int field, const double* x);
 int msgpu_macro_get_solution(msgpu_ctx* ctx, int field, double* x);
 int msgpu_macro_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int adopt, int* iters);
 
+/* ---- the stop test on the device -----------------------------------------------------------
+ * MicroSolver::compute_all_errors / compute_all_residuals (micro.cpp:186-215, bio micro.cpp:317-378) aggregate the
+ * per-grid norms as a NODAL function on the macro mesh and take its L2 norm (integrate_difference against zero +
+ * compute_global_error); MacroSolver::compute_residual (bio macro.cpp:230-245) does the same with a macro vector.
+ *   msgpu_norm_setup         the macro mesh once: cell_dofs[n_cells][4] (vertex order (0,0),(1,0),(0,1),(1,1); indices
+ *                            into vectors with one value per grid location, n_values of them), cell side h
+ *   msgpu_norm_of_values     that norm of a host vector values[n_values], QGauss(q)
+ *   msgpu_norm_of_residuals  ... of the per-grid ||v_k - v_k_old|| (as msgpu_residuals), computed, allgathered over
+ *                            the ranks (NCCL) and aggregated without leaving the device
+ *   msgpu_norm_of_errors     ... of the per-grid L2 and H1 errors (as msgpu_errors)
+ * Cells, points and the sum over the cells keep the caller's order and the host's arithmetic (no FMA contraction):
+ * the values equal those of the host loop they replace.  MSGPU_ERR_UNSUPPORTED: several ranks without an NCCL
+ * communicator (ranks that share a device) - the caller aggregates on the host then.                          */
+int msgpu_norm_setup(msgpu_ctx* ctx, const int* cell_dofs, int n_cells, int n_values, double h);
+int msgpu_norm_of_values(msgpu_ctx* ctx, const double* values, int q, double* out);
+int msgpu_norm_of_residuals(msgpu_ctx* ctx, int q, double* out);
+int msgpu_norm_of_errors(msgpu_ctx* ctx, int q, double* l2, double* h1);
+
 /* ---- measurement hooks ------------------------------------------------------------------- */
 typedef struct {
   double ms_tables;    /* slot + line table kernels                    */

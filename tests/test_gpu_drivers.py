@@ -236,3 +236,36 @@ def test_pi_solver_load_on_the_device_equals_the_host_assembly(prm):
     assert out["device"][0] == out["host"][0] and len(out["device"][1]) == len(out["host"][1])
     for (pa, ma, ra), (pb, mb, rb) in zip(out["device"][1], out["host"][1]):
         assert rel_l2(pa, pb) < 1e-11 and rel_l2(ma, mb) < 1e-11 and rel_l2(ra, rb) < 1e-11
+
+
+@pytest.mark.parametrize("prm,cells,limit", [("linear.prm", (4, 8), 4), ("biocase.prm", (4, 8), 4)])
+def test_stop_test_on_the_device_equals_the_host_aggregation(prm, cells, limit):
+    """The macro-aggregated error / residual norms that decide the stop (bio manager.cpp:70-109) are computed by
+    msgpu_norm_* without copying the per-grid scalars to the host: same cells, same points, same order and no FMA
+    contraction, so the scalars of every cycle EQUAL those of the host loop (MSGPU_HOST_STOP_TEST=1) bit for bit."""
+    lib = _drivers()
+    out = {}
+    for name, env in (("device", None), ("host", "1")):
+        if env:
+            os.environ["MSGPU_HOST_STOP_TEST"] = env
+        try:
+            h = C.c_void_p(lib.msdrv_bio_create(_path(prm), *cells))
+            assert h.value, lib.msdrv_last_error()
+            n_cycles = lib.msdrv_bio_run(h, limit)
+            N, n = C.c_int(), C.c_int()
+            lib.msdrv_bio_sizes(h, C.byref(N), C.byref(n))
+            N, n = N.value, n.value
+            scalars = []
+            for c in range(n_cycles):
+                sc = np.zeros(6)
+                u, w, cu, cw = np.zeros(N), np.zeros(N), np.zeros(N), np.zeros(N)
+                micro, its = np.zeros((N, n)), np.zeros(N, dtype=np.int32)
+                lib.msdrv_bio_history(h, c, dptr(sc), dptr(u), dptr(w), dptr(cu), dptr(cw), dptr(micro), iptr(its))
+                scalars.append(sc.copy())
+            out[name] = (n_cycles, np.array(scalars))
+            lib.msdrv_bio_destroy(h)
+        finally:
+            os.environ.pop("MSGPU_HOST_STOP_TEST", None)
+    assert out["device"][0] == out["host"][0]
+    assert np.array_equal(out["device"][1], out["host"][1]), (out["device"][1], out["host"][1])
+    assert np.abs(out["device"][1]).max() > 0
