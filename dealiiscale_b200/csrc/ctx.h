@@ -103,6 +103,10 @@ struct msgpu_ctx {
 
   // state
   int setup_done = 0, assembled = 0, tables_valid = 0;
+  // MSGPU_REUSE_ASSEMBLY=1 (opt-in, read at msgpu_create): matrices, macro-independent loads and boundary data do not
+  // depend on the macro solution, so after the first msgpu_assemble of a set-up only the right-hand sides are
+  // refreshed.  Off by default: the reference re-assembles in every cycle and so does the default path.
+  int reuse_assembly = 0, assembly_cached = 0;
   double tables_time = 0.0;
   std::vector<int> h_iters;
   long long cg_iterations_total = 0;

@@ -119,3 +119,43 @@ def test_linearity_of_the_micro_solution_in_the_macro_values():
     d1, d2 = sols[1] - sols[0], sols[2] - sols[0]
     assert rel_l2(d2, 2 * d1) < 1e-8
     ms.close()
+
+
+def test_reuse_of_the_macro_independent_assembly_is_bit_identical(monkeypatch):
+    """MSGPU_REUSE_ASSEMBLY=1 (opt-in): matrices and macro-independent loads are assembled once per set-up, later
+    msgpu_assemble calls only refresh the right-hand sides (the reference re-assembles every cycle,
+    bio micro.cpp:292-305, although only b depends on u, w).  Same solutions, bit for bit, and a new set of scalars
+    still triggers a full assembly."""
+    from dealiiscale_b200 import capi
+    from dealiiscale_b200.micro import MicroSolver
+    from dealiiscale_b200.prm import BioData
+
+    data = BioData(os.path.join(INPUT, "biocase-curved.prm"))
+    g = np.linspace(-0.9, 0.9, 3)
+    xy = np.array([(a, b) for b in g for a in g])
+    macro = [(np.sin(xy[:, 0]), np.cos(xy[:, 1])), (xy[:, 0] * 0.5, xy[:, 1] - 0.2), (xy[:, 1] ** 2, xy[:, 0] + 1.0)]
+    results = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MSGPU_REUSE_ASSEMBLY", mode)
+        ms = MicroSolver(capi.BIO, data, 16)
+        ms.set_grid_locations(xy)
+        ms.setup()
+        ms.enable_timing(True)
+        out = []
+        for u, w in macro:
+            ms.set_macro_solution(u, w)
+            ms.zero_solutions()
+            ms.run()
+            out.append((ms.solutions().copy(), ms.righthandsides().copy(), np.array(ms.coupling())))
+        moments_ms = ms.stats()["ms_moments"]
+        sc = np.array(data.scalars(), dtype=float)
+        sc[1] *= 2.0
+        ms.set_scalars(sc)  # another Robin coefficient: the cached matrices are stale
+        ms.zero_solutions()
+        ms.run()
+        out.append((ms.solutions().copy(), ms.righthandsides().copy(), np.array(ms.coupling())))
+        results[mode] = (out, moments_ms)
+        ms.close()
+    for (xa, ba, ca), (xb, bb, cb) in zip(results["0"][0], results["1"][0]):
+        assert np.array_equal(xa, xb) and np.array_equal(ba, bb) and np.array_equal(ca, cb)
+    assert results["1"][1] < 0.6 * results["0"][1]  # two of the three assemblies did no moment work
