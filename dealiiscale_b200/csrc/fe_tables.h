@@ -66,6 +66,26 @@ inline std::vector<double> build_qtab(int q, const std::vector<double>& pt, cons
   return t;
 }
 
+// 1-D factors of the table above: every entry of build_qtab is (a function of xi) * (a function of eta), so the
+// moments of a cell are summed row by row - the xi factor at every point, the eta factor once per row:
+//   row 0, 1   w (1 - s), w s                      (shape values; mixed-derivative products)
+//   row 2..4   w (1 - s)^2, w (1 - s) s, w s^2     (products of two derivatives in the other direction)
+//   row 5      w
+// entry [r * q + i] for the i-th Gauss point s = pt[i], w = wt[i].
+inline std::vector<double> build_q1d(int q, const std::vector<double>& pt, const std::vector<double>& wt) {
+  std::vector<double> t(static_cast<size_t>(Q1D_ROWS) * q);
+  for (int i = 0; i < q; ++i) {
+    const double s = pt[i], sb = 1 - pt[i], w = wt[i];
+    t[0 * q + i] = w * sb;
+    t[1 * q + i] = w * s;
+    t[2 * q + i] = w * (sb * sb);
+    t[3 * q + i] = w * (sb * s);
+    t[4 * q + i] = w * (s * s);
+    t[5 * q + i] = w;
+  }
+  return t;
+}
+
 // Reference DoF numbering of FE_Q(1): DoFs are numbered in the order the active cells first
 // touch their vertices, local vertex order (0,0),(1,0),(0,1),(1,1).  Active cells of
 // hyper_cube+refine_global come in Morton order (child index = cx_bit + 2*cy_bit per level),

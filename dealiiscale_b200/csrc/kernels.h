@@ -30,6 +30,7 @@ struct Tables {
 constexpr int CELL_STRIDE = 18;  // 10 local matrix entries, 4 load entries, 4 det-weighted basis integrals
 constexpr int FACE_STRIDE = 7;   // Robin mass (aa, ab, bb), load (a, b), stretch weights (a, b)
 constexpr int QTAB_STRIDE = 14; // see fe_tables.h build_qtab
+constexpr int Q1D_ROWS = 6;     // see fe_tables.h build_q1d
 constexpr int NDIAG = 5;         // stored diagonals: offsets 0, +1, +m-1, +m, +m+1
 
 enum ProblemFlags : int {
@@ -66,7 +67,7 @@ struct MomentPrograms {
 int launch_cell_moments(cudaStream_t s, const MomentPrograms& mp, MeshDims md, Tables tb, const double* qtab,
                         const double* qsum, int k0, int nk, double stiffness_scale, double* cell, int* error_flag);
 // one-time upload of the per-quadrature-point tables into constant memory (q = 2, 3, 12)
-int upload_constant_tables(int q, const double* qtab, const double* qsum);
+int upload_constant_tables(int q, const double* qtab, const double* qsum, const double* q1d);
 
 // K1 faces: for systems [k0,k0+nk) and side in {0:x=-1, 1:x=+1, 2:y=-1, 3:y=+1} writes
 // face[((kl*4 + side)*FACE_STRIDE + e)*nc + f].  One program per side: outputs F00..F11, BC.

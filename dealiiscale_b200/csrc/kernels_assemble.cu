@@ -36,27 +36,32 @@ __constant__ double c_qtab3[9 * QTAB_STRIDE];
 __constant__ double c_qsum3[QTAB_STRIDE];
 __constant__ double c_qtab2[4 * QTAB_STRIDE];
 __constant__ double c_qsum2[QTAB_STRIDE];
+__constant__ double c_q1d12[Q1D_ROWS * 12];  // fe_tables.h build_q1d
+__constant__ double c_q1d3[Q1D_ROWS * 3];
+__constant__ double c_q1d2[Q1D_ROWS * 2];
 
 template <int Q>
 struct TabConst;
 #ifdef __CUDA_ARCH__
-#define MSGPU_CONST_TAB(Q, TAB, SUM)                                                        \
+#define MSGPU_CONST_TAB(Q, TAB, SUM, LINE)                                                  \
   template <>                                                                               \
   struct TabConst<Q> {                                                                      \
     __host__ __device__ double operator()(int q, int i) const { return TAB[q * QTAB_STRIDE + i]; } \
     __host__ __device__ double total(int i) const { return SUM[i]; }                        \
+    __host__ __device__ double line(int r, int i) const { return LINE[r * Q + i]; }         \
   };
 #else
-#define MSGPU_CONST_TAB(Q, TAB, SUM)                                                        \
+#define MSGPU_CONST_TAB(Q, TAB, SUM, LINE)                                                  \
   template <>                                                                               \
   struct TabConst<Q> {                                                                      \
     __host__ __device__ double operator()(int, int) const { return 0.0; }                   \
     __host__ __device__ double total(int) const { return 0.0; }                             \
+    __host__ __device__ double line(int, int) const { return 0.0; }                         \
   };
 #endif
-MSGPU_CONST_TAB(12, c_qtab12, c_qsum12)
-MSGPU_CONST_TAB(3, c_qtab3, c_qsum3)
-MSGPU_CONST_TAB(2, c_qtab2, c_qsum2)
+MSGPU_CONST_TAB(12, c_qtab12, c_qsum12, c_q1d12)
+MSGPU_CONST_TAB(3, c_qtab3, c_qsum3, c_q1d3)
+MSGPU_CONST_TAB(2, c_qtab2, c_qsum2, c_q1d2)
 
 template <int Q, int W, int MODE>
 __global__ void __launch_bounds__(TB) k_cell_moments_vec(const __grid_constant__ VmProgram progF,
@@ -219,18 +224,22 @@ int launch_cell_moments(cudaStream_t s, const MomentPrograms& mp, MeshDims md, T
   return 1;
 }
 
-int upload_constant_tables(int q, const double* qtab, const double* qsum) {
+int upload_constant_tables(int q, const double* qtab, const double* qsum, const double* q1d) {
   cudaError_t e = cudaSuccess;
   const size_t bytes = static_cast<size_t>(q) * q * QTAB_STRIDE * sizeof(double), sb = QTAB_STRIDE * sizeof(double);
+  const size_t lb = static_cast<size_t>(Q1D_ROWS) * q * sizeof(double);
   if (q == 12) {
     e = cudaMemcpyToSymbol(c_qtab12, qtab, bytes);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_qsum12, qsum, sb);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_q1d12, q1d, lb);
   } else if (q == 3) {
     e = cudaMemcpyToSymbol(c_qtab3, qtab, bytes);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_qsum3, qsum, sb);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_q1d3, q1d, lb);
   } else if (q == 2) {
     e = cudaMemcpyToSymbol(c_qtab2, qtab, bytes);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_qsum2, qsum, sb);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_q1d2, q1d, lb);
   }
   return e == cudaSuccess ? 0 : 1;
 }

@@ -333,7 +333,8 @@ int msgpu_setup(msgpu_ctx* ctx) {
   std::vector<double> qsum(QTAB_STRIDE, 0.0);
   for (int q = 0; q < md.q * md.q; ++q)
     for (int i = 0; i < QTAB_STRIDE; ++i) qsum[i] += qtab[static_cast<size_t>(q) * QTAB_STRIDE + i];
-  if (upload_constant_tables(md.q, qtab.data(), qsum.data()))
+  const std::vector<double> q1d = build_q1d(md.q, pt, wt);
+  if (upload_constant_tables(md.q, qtab.data(), qsum.data(), q1d.data()))
     return fail(ctx, MSGPU_ERR_CUDA, "cannot upload the quadrature tables to constant memory");
   // Specialise the cell-moment kernel for this problem's expressions (elliptic and bio assemble
   // every cycle).  Any failure leaves the interpreter kernels in charge and is kept in jit_log.
@@ -388,9 +389,10 @@ int msgpu_setup(msgpu_ctx* ctx) {
   if ((rc = dev_alloc(ctx, &ctx->d_qtab, qtab.size() + QTAB_STRIDE))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_q1pt, static_cast<size_t>(md.q)))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_q1wt, static_cast<size_t>(md.q)))) return rc;
-  // chunk of systems whose cell / face moments are in flight at once (<= 2 GiB of scratch)
+  // chunk of systems whose cell / face moments are in flight at once (<= 6 GiB of scratch of the 180 GB: the 4225
+  // systems of `6 6` are one chunk - two launches per kernel instead of four, no second short tail)
   const size_t per_system = static_cast<size_t>(CELL_STRIDE) * md.ncells * sizeof(double);
-  size_t chunk = (static_cast<size_t>(2) << 30) / per_system;
+  size_t chunk = (static_cast<size_t>(6) << 30) / per_system;
   if (const char* e = std::getenv("MSGPU_CHUNK")) chunk = static_cast<size_t>(std::atol(e));
   chunk = std::max<size_t>(1, std::min<size_t>(chunk, N));
   ctx->chunk = static_cast<int>(chunk);

@@ -142,13 +142,25 @@ class MacroSolver {
   }
   void assemble_and_solve() {
     if (on_device) {
+      const char* tm = std::getenv("MSGPU_DRIVER_TIMING");
+      const bool fine = tm && tm[0] == '2';
+      const auto t0 = std::chrono::steady_clock::now();
       compute_microscopic_contribution();  // integrals stay on the device; host copies are for the records
       old_sol_u = sol_u;
       old_sol_w = sol_w;
+      const auto t1 = std::chrono::steady_clock::now();
+      std::vector<int> its;
       if (micro->solves_macro_here()) {
-        micro->macro_solve(1e-12, 10000, true);
+        its = micro->macro_solve(1e-12, 10000, true);
+        const auto t2 = std::chrono::steady_clock::now();
         micro->macro_get_solution(0, sol_u);
         micro->macro_get_solution(1, sol_w);
+        if (fine) {
+          const auto t3 = std::chrono::steady_clock::now();
+          auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+          std::printf("[timing2] macro: integrals to host %.3f ms, rhs + CG (%d, %d steps) + adopt %.3f ms, solutions to host %.3f ms\n",
+                      ms(t0, t1), its.size() > 0 ? its[0] : 0, its.size() > 1 ? its[1] : 0, ms(t1, t2), ms(t2, t3));
+        }
       }
       micro->share_macro_solution(sol_u, &sol_w);
       return;
@@ -355,8 +367,14 @@ class Manager {
       std::printf("Old error %.2e, new error %.2e\n", old_error, error);
       reached = std::fabs(old_error - error) / error < error_eps;
     } else {
+      const auto ts0 = std::chrono::steady_clock::now();
       macro_solver.compute_residual(r.macro_residual);
+      const auto ts1 = std::chrono::steady_clock::now();
       micro_solver.compute_all_residuals(macro_solver.mesh, 12, r.micro_residual);
+      if (const char* tm = std::getenv("MSGPU_DRIVER_TIMING"); tm && tm[0] == '2')
+        std::printf("[timing2] stop test: macro residual %.3f ms, micro residuals %.3f ms\n",
+                    std::chrono::duration<double, std::milli>(ts1 - ts0).count(),
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts1).count());
       old_residual = residual;
       std::printf("Macro residual: %.2e\tMicro residual: %.2e\n", r.macro_residual, r.micro_residual);
       residual = r.macro_residual + r.micro_residual;

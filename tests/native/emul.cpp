@@ -37,7 +37,7 @@ struct Emul {
   std::string err;
   int jac_flag = 0;
   int vector_vm = 1;  // 1: the vectorised moments body (what the product launches for q = 2, 3, 12)
-  std::vector<double> qsum;
+  std::vector<double> qsum, q1d;
   std::vector<double> R;
   Tables tables() const {
     Tables tb;
@@ -168,6 +168,7 @@ int emul_setup(void* h, const double* xy, int N, double t) {
   e->xy.assign(xy, xy + 2 * N);
   gauss_legendre_unit(md.q, e->q1pt, e->q1wt);
   e->qtab = build_qtab(md.q, e->q1pt, e->q1wt);
+  e->q1d = build_q1d(md.q, e->q1pt, e->q1wt);
   e->qsum.assign(QTAB_STRIDE, 0.0);
   for (int q = 0; q < md.q * md.q; ++q)
     for (int i = 0; i < QTAB_STRIDE; ++i) e->qsum[i] += e->qtab[static_cast<size_t>(q) * QTAB_STRIDE + i];
@@ -281,7 +282,7 @@ int emul_assemble(void* h, const double* u, const double* w) {
   const VmProgram& volG = ps.point_program(e->pp.prog_vol_G);
   const VmProgram& volF = e->pp.prog_vol_F >= 0 ? ps.point_program(e->pp.prog_vol_F) : vol;
   const int mode = emul_moment_mode(e);
-  const TabGlobal tab{e->qtab.data(), e->qsum.data()};
+  const TabGlobal tab{e->qtab.data(), e->qsum.data(), e->q1d.data(), md.q};
   const long long work = static_cast<long long>(N) * md.ncells;
   auto run_vec = [&](auto Qc, auto Wc) {
     constexpr int Q = decltype(Qc)::value, W = decltype(Wc)::value;
@@ -632,7 +633,7 @@ int emul_parabolic_step(void* h, const double* u, double dt, double t, double to
   rebuild_tables(e, t);
   Tables tb = e->tables();
   const VmProgram& volG = ps.point_program(e->pp.prog_vol_G);
-  const TabGlobal tab{e->qtab.data(), e->qsum.data()};
+  const TabGlobal tab{e->qtab.data(), e->qsum.data(), e->q1d.data(), md.q};
   for (long long g = 0; g < static_cast<long long>(N) * md.ncells; ++g) {
     if (md.q == 2)
       body_cell_moments_vec<2, 2, MODE_NO_MAP>(volG, volG, md, tb, tab, 0, N, 1.0, e->cell.data(), &e->jac_flag, g,
