@@ -462,12 +462,19 @@ def driver_cycle(args, rank, world, dist, reuse_assembly=False):
                 "strong": {
                     "scaling": "strong", "n_gpus": world, "macro_points_total": (Mc + 1) ** 2,
                     "metric": METRIC, "unit": UNIT,
+                    # whole cycles after the first (the first also pays one-off allocations and lazy module loads)
+                    "value": work / (float(np.median(cyc[later])) * 1e-3),
+                    "ms_cycle": float(np.median(cyc[later])),
+                    "ms_micro": float(np.median(micro[later])), "ms_macro": float(np.median(macro[later])),
+                    "ms_stop_test": float(np.median(stop[later])),
+                    "micro_phase_value": work / (float(np.median(micro[later])) * 1e-3),
+                    "value_later_cycles": work / (float(np.median(cyc[later])) * 1e-3),
                     "value_first_cycle": work / (cyc[0] * 1e-3),
                     "micro_phase_value_first_cycle": work / (micro[0] * 1e-3),
-                    "value_later_cycles": work / (float(np.median(cyc[later])) * 1e-3),
                     "ms_cycle_first": cyc[0], "ms_micro_first": micro[0],
-                    "note": "whole fixed-point cycle of the real driver on the literal lattice; cycle 1 solves from a zero start "
-                            "like the weak-scaling step, later cycles warm-start (fewer CG steps)",
+                    "note": "whole fixed-point cycle of the real driver on the literal lattice (4225 macro points in total, "
+                            "sharded over the GPUs of the job); medians over the cycles after the first, which warm-start "
+                            "(fewer CG steps than the zero start of cycle 1 and of the weak-scaling step)",
                 },
             }
         shutil.rmtree(box[0], ignore_errors=True)

@@ -352,6 +352,11 @@ class CodeGen {
   void finish() {
     emit(vm_encode(OP_END, 0, 0));
     p_.n_regs = high_water_;
+    p_.reads_lines = mode_ == MODE_POINTS ? 1 : 0;  // MODE_POINTS: y0, y1 are per-thread inputs
+    for (int pc = 0; pc < p_.n_code; ++pc) {
+      const uint32_t op = p_.code[pc] & 0xffu, kind = (p_.code[pc] >> 8) & 7u;
+      if (op != OP_END && op <= OP_LAST_BINARY && (kind == VK_LINE0 || kind == VK_LINE1)) p_.reads_lines = 1;
+    }
   }
 
  private:

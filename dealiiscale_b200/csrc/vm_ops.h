@@ -52,7 +52,7 @@ struct VmProgram {
   int n_code;
   int n_regs;  // per-thread registers the program touches (inputs + outputs + temporaries)
   int out0;    // first output register of a point program (0 in MODE_LINES, 2 in MODE_POINTS)
-  int pad_;
+  int reads_lines;  // 0: no operand comes from a line table - the outputs of a point program are the same at every point
   uint32_t code[VM_MAX_CODE];
   double consts[VM_MAX_CONST];
 };
