@@ -80,6 +80,42 @@ def build_msgpu(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+CHECKED_LIB = os.path.join(BUILD, "libmsgpu_checked.so")
+CHECKED_SOURCES = ("kernels_cg.cu", "kernels_cg_stencil.cu")
+
+
+def build_checked(force: bool = False) -> str:
+    """TEST INFRASTRUCTURE: libmsgpu_checked.so, the product's objects with the CG kernels compiled -DMSGPU_CHECKED
+    (csrc/checked.cuh: every shared-, distributed-shared- and tensor-memory access of the resident CG kernels is
+    compared with the window it may touch and traps otherwise).  tests/test_gpu_checked_build.py runs the kernels
+    through it; nothing in the product loads it."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    build_msgpu()
+    files, deps = _sources()
+    objdir = os.path.join(BUILD, "obj")
+    newest_dep = _newest(deps)
+    objs, jobs = [], []
+    for src in files:
+        base = os.path.basename(src)
+        obj = os.path.join(objdir, base + ".o")
+        if base in CHECKED_SOURCES:
+            obj = os.path.join(objdir, base + ".checked.o")
+            if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_dep):
+                jobs.append([_nvcc()] + NVCC_FLAGS + ["-DMSGPU_CHECKED", "-c", src, "-o", obj])
+        objs.append(obj)
+    if not jobs and os.path.exists(CHECKED_LIB) and os.path.getmtime(CHECKED_LIB) >= os.path.getmtime(LIB):
+        return CHECKED_LIB
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        for res in pool.map(lambda c: subprocess.run(c, cwd=CSRC, capture_output=True, text=True), jobs):
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed (checked build):\n" + res.stdout + res.stderr)
+    res = subprocess.run([_nvcc(), "-shared", "-o", CHECKED_LIB] + objs + ["-ldl"], cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed (checked build):\n" + res.stdout + res.stderr)
+    return CHECKED_LIB
+
+
 def build_oracle() -> str:
     """TEST INFRASTRUCTURE: the CPU restatement of the reference (oracle/)."""
     subprocess.check_call(["make", "-s"], cwd=os.path.join(ROOT, "oracle"))
@@ -101,6 +137,7 @@ def build_host_drivers() -> None:
 
 def build_all(force: bool = False) -> None:
     build_msgpu(force=force)
+    build_checked(force=force)
     build_oracle()
     build_emul()
     build_host_drivers()
@@ -110,6 +147,7 @@ if __name__ == "__main__":
     import sys
 
     build_msgpu(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_checked(force="--force" in sys.argv)
     build_oracle()
     build_emul()
     build_host_drivers()

@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "cg_common.cuh"
+#include "checked.cuh"
 #include "kernels.h"
 
 namespace msgpu {
@@ -614,8 +615,9 @@ __global__ void __launch_bounds__(BT, 512 / tmem_alloc_columns(BT, K)) k_cg_stri
   const int pad = tmem_pad(m, K);  // >= m + 1 + K: dead rows n..n+K-1 stay inside the guards
   const int ms = pad + ld;
   // shared memory: M1..M4 (4 diagonals) + d with halos + reduction scratch
-  double* const mat = sm;
-  double* const dv = sm + 4 * ms + pad;
+  // (checked builds, checked.cuh: every access below is compared with the window it may touch)
+  const CheckedPtr<double> mat = checked(sm, sm, sm + 4 * ms);
+  const CheckedPtr<double> dv = checked(sm + 4 * ms + pad, sm + 4 * ms, sm + 4 * ms + n + 2 * pad);
   double* const red = sm + ((4 * ms + n + 2 * pad + 1) & ~1);  // 16-byte aligned
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r0 = tid * K;
@@ -640,10 +642,13 @@ __global__ void __launch_bounds__(BT, 512 / tmem_alloc_columns(BT, K)) k_cg_stri
   const uint32_t tbase =
       s_tmem + ((static_cast<uint32_t>(warp & 3) * 32u) << 16) + static_cast<uint32_t>(warp >> 2) * static_cast<uint32_t>(CW);
 
-  const double* const M1 = mat + pad;
-  const double* const M2 = M1 + ms;
-  const double* const M3 = M2 + ms;
-  const double* const M4 = M3 + ms;
+  const CheckedPtr<const double> M1 = mat + pad;
+  const CheckedPtr<const double> M2 = M1 + ms;
+  const CheckedPtr<const double> M3 = M2 + ms;
+  const CheckedPtr<const double> M4 = M3 + ms;
+  // tensor memory: rows j = 0 .. K-1 of this thread at columns tbase + 14 j .. + 15, inside the CW columns of the warp
+  [[maybe_unused]] const uint32_t tm_lo = tbase & 0xffffu, tm_hi = tm_lo + CW;
+  MSGPU_CHECK((warp >> 2) * CW + CW <= ALLOC);
 
   // h = A d for the K rows of this thread; dl = own entries of d (registers), dv = all of d (shared)
   auto spmv_strip = [&](const double (&dl)[K], double (&hh)[K]) {
@@ -653,13 +658,17 @@ __global__ void __launch_bounds__(BT, 512 / tmem_alloc_columns(BT, K)) k_cg_stri
     double below = dv[rc0 - 1];
     double m1_prev = M1[rc0 - 1];
     TmemRow q[2];  // double buffer; the loop is fully unrolled, so q[j & 1] are plain registers
+    MSGPU_CHECK_TMEM(tbase, 16u, tm_lo, tm_hi);
     tmem_issue_row(tbase, q[0]);
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       const int r = rc0 + j;
       TmemRow& cur = q[j & 1];
       tmem_wait_row(cur);
-      if (j + 1 < K) tmem_issue_row(tbase + 14u * (j + 1), q[(j + 1) & 1]);  // one row ahead
+      if (j + 1 < K) {
+        MSGPU_CHECK_TMEM(tbase + 14u * (j + 1), 16u, tm_lo, tm_hi);
+        tmem_issue_row(tbase + 14u * (j + 1), q[(j + 1) & 1]);  // one row ahead
+      }
       const double rc = dv[r + m + 1], lc = dv[r - m + 1];
       const double m1 = M1[r];
       const double above = (j + 1 < K) ? dl[j + 1] : dv[r + 1];
@@ -702,7 +711,7 @@ __global__ void __launch_bounds__(BT, 512 / tmem_alloc_columns(BT, K)) k_cg_stri
   bool have_matrix = false;
   // Jacobi: reciprocal diagonal in the staging area of M2 (free once the matrix sits in tensor memory): no extra
   // registers in the CG loop, a multiplication instead of a division per row
-  double* const rdiag = mat + ms + pad;
+  const CheckedPtr<double> rdiag = mat + (ms + pad);
   double d0[JACOBI ? K : 1];  // transient: the diagonal of this strip between packing and the barrier
   for (;;) {
     __syncthreads();
@@ -734,7 +743,7 @@ __global__ void __launch_bounds__(BT, 512 / tmem_alloc_columns(BT, K)) k_cg_stri
     if (load_matrix) {
       for (int d = 1; d < NDIAG; ++d) {
         const double* src = dg + static_cast<size_t>(d) * ld;
-        double* dst = mat + (d - 1) * ms + pad;
+        const CheckedPtr<double> dst = mat + ((d - 1) * ms + pad);
         for (int r = tid; r < n; r += BT) dst[r] = __ldg(src + r);
       }
       for (int r = tid; r < n; r += BT) dv[r] = __ldg(dg + r);
@@ -754,6 +763,7 @@ __global__ void __launch_bounds__(BT, 512 / tmem_alloc_columns(BT, K)) k_cg_stri
       v[5] = in ? M3[r - m] : 0.0;
       v[6] = in ? M4[r - (m + 1)] : 0.0;
       if (JACOBI) d0[j] = in ? v[0] : 1.0;
+      MSGPU_CHECK_TMEM(tbase + 14u * j, 16u, tm_lo, tm_hi);
       tmem_store_row(tbase + 14u * j, v);  // ascending j: the two surplus columns are rewritten by row j+1
     }
     __syncthreads();  // everybody has picked up M0 before d is overwritten
@@ -911,16 +921,22 @@ __global__ void __launch_bounds__(256, 1) k_cg_cluster(CgArgs a) {
   const int win = RC + 2 * pad;            // window of this CTA: local index i in [-pad, RC + pad)
   const int lo = crank * RC;               // first global row of this CTA
   const int nloc = n - lo < RC ? (n - lo > 0 ? n - lo : 0) : RC;
-  double* const m1 = sm + pad;             // M1[lo + i]
-  double* const dv = sm + win + pad;       // d[lo + i]
+  // (checked builds, checked.cuh: every access, local or in a neighbour's shared memory, is compared with its window)
+  const CheckedPtr<double> m1 = checked(sm + pad, sm, sm + win);                   // M1[lo + i]
+  const CheckedPtr<double> dv = checked(sm + win + pad, sm + win, sm + 2 * win);  // d[lo + i]
   double* const red = sm + 2 * win;        // 3 x 32 warp partials (16-byte aligned: 2*win is even)
   double* const cred = red + 96;           // 3 x 8 CTA partials
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r0 = tid * K;                                         // local
   const int rc0 = r0 < nloc ? r0 : nloc;                          // dead threads sit on the zero guard
   const int nlive = r0 < nloc ? (nloc - r0 < K ? nloc - r0 : K) : 0;
-  double* const dv_prev = crank > 0 ? cluster.map_shared_rank(dv, crank - 1) : nullptr;
-  double* const dv_next = crank + 1 < CL ? cluster.map_shared_rank(dv, crank + 1) : nullptr;
+  // the same window of d in the neighbours' shared memory (distributed shared memory)
+  auto remote_dv = [&](int rank) -> CheckedPtr<double> {
+    double* const rsm = cluster.map_shared_rank(sm, rank);
+    return checked(rsm + win + pad, rsm + win, rsm + 2 * win);
+  };
+  const CheckedPtr<double> dv_prev = crank > 0 ? remote_dv(crank - 1) : checked<double>(nullptr, nullptr, nullptr);
+  const CheckedPtr<double> dv_next = crank + 1 < CL ? remote_dv(crank + 1) : checked<double>(nullptr, nullptr, nullptr);
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(
@@ -933,6 +949,7 @@ __global__ void __launch_bounds__(256, 1) k_cg_cluster(CgArgs a) {
   asm volatile("tcgen05.fence::after_thread_sync;\n");
   const uint32_t tbase =
       s_tmem + ((static_cast<uint32_t>(warp & 3) * 32u) << 16) + static_cast<uint32_t>(warp >> 2) * static_cast<uint32_t>(CW);
+  [[maybe_unused]] const uint32_t tm_lo = tbase & 0xffffu, tm_hi = tm_lo + CW;
 
   // own entries of d -> shared memory, border entries also into the neighbours' halos
   auto publish = [&](const double (&dl)[K]) {
@@ -953,13 +970,17 @@ __global__ void __launch_bounds__(256, 1) k_cg_cluster(CgArgs a) {
     double below = dv[rc0 - 1];
     double m1_prev = m1[rc0 - 1];
     TmemRow q[2];
+    MSGPU_CHECK_TMEM(tbase, 16u, tm_lo, tm_hi);
     tmem_issue_row(tbase, q[0]);
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       const int r = rc0 + j;
       TmemRow& cur = q[j & 1];
       tmem_wait_row(cur);
-      if (j + 1 < K) tmem_issue_row(tbase + 14u * (j + 1), q[(j + 1) & 1]);
+      if (j + 1 < K) {
+        MSGPU_CHECK_TMEM(tbase + 14u * (j + 1), 16u, tm_lo, tm_hi);
+        tmem_issue_row(tbase + 14u * (j + 1), q[(j + 1) & 1]);
+      }
       const double rc = dv[r + m + 1], lc = dv[r - m + 1];
       const double m1r = m1[r];
       const double above = (j + 1 < K) ? dl[j + 1] : dv[r + 1];
@@ -1019,6 +1040,7 @@ __global__ void __launch_bounds__(256, 1) k_cg_cluster(CgArgs a) {
       v[5] = (in && g - m >= 0) ? __ldg(dg + 3 * static_cast<size_t>(ld) + g - m) : 0.0;
       v[6] = (in && g - (m + 1) >= 0) ? __ldg(dg + 4 * static_cast<size_t>(ld) + g - (m + 1)) : 0.0;
       if (JACOBI) diag_own[j] = in ? v[0] : 1.0;
+      MSGPU_CHECK_TMEM(tbase + 14u * j, 16u, tm_lo, tm_hi);
       tmem_store_row(tbase + 14u * j, v);
     }
 

@@ -38,6 +38,7 @@
 #include <type_traits>
 
 #include "cg_common.cuh"
+#include "checked.cuh"
 #include "kernels.h"
 
 namespace msgpu {
@@ -46,6 +47,10 @@ namespace {
 
 using cgc::l2_prefetch_bulk;
 using cgc::warp_sum;
+
+#ifdef MSGPU_CHECKED
+__device__ int g_checked_selftest = 0;  // MSGPU_CHECKED_SELFTEST=1: one deliberate out-of-window read (tests)
+#endif
 
 constexpr int ST_MAX_THREADS = 256;  // 8 warps: 255 registers (one CTA per SM) or 128 (two, vectors in tensor memory)
 constexpr int ST_RED = 8;            // slots of one reduction buffer (= warps per CTA)
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
   const int mp = p.mp, P = p.P, m = a.md.m, n = a.md.n, off = p.off, ov = p.ov;
   const int dvlen = (2 + (mp + 2 * W + 2) * P + 1) & ~1;
-  double* const dv = sm + 2 + P;   // everything nobody writes stays zero
+  const CheckedPtr<double> dv = checked(sm + 2 + P, sm, sm + dvlen);  // everything nobody writes stays zero
   double* const red = sm + dvlen;  // 3 x ST_RED, 16-byte aligned
   double* const tab = red + 3 * ST_RED;
 
@@ -262,7 +267,10 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
   const bool live = tid < p.S * p.TC;  // idle threads sit on columns mp + W - 1 ...: zeros there and on both sides
   const int ix0 = live ? tcol * W : mp + W - 1;
   const bool first = live && s == 0, last = live && s == p.S - 1;
-  double* const dvt = dv + ix0 * P + (live ? (last ? mp - KR : s * KR) : 0);  // node (0, 0) of the tile
+  const CheckedPtr<double> dvt = dv + (ix0 * P + (live ? (last ? mp - KR : s * KR) : 0));  // node (0, 0) of the tile
+#ifdef MSGPU_CHECKED
+  if (g_checked_selftest && tid == 0 && dv[-(2 + P) - 1] == 1.2345e-300) return;  // must trip the window check
+#endif
   bool col_live[W];  // tile columns past the mesh compute zeros and write nothing
 #pragma unroll
   for (int c = 0; c < W; ++c) col_live[c] = live && (DCN == 0 || ix0 + c < mp);
@@ -293,7 +301,11 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
            static_cast<uint32_t>(warp >> 2) * static_cast<uint32_t>(p.cw);
     gcol = xcol + 2u * E;
     hcol = xcol + 4u * E;
+    MSGPU_CHECK(6 * E <= p.cw && (warp >> 2) * p.cw + p.cw <= p.alloc);
   }
+  // checked builds: every tensor-memory access must stay inside the 6 E columns of this warp
+  [[maybe_unused]] const uint32_t tm_lo = xcol & 0xffffu, tm_hi = tm_lo + 6u * E;
+#define MSGPU_TM(a, nd) MSGPU_CHECK_TMEM(a, 2u * (nd), tm_lo, tm_hi)
 
   double xx[W][KR], gg[W][KR], dl[W][KR], hh[W][KR];  // solution, residual, search direction, A d: this thread's tile
                                                       // (TM: only dl; the others live in tensor memory)
@@ -370,6 +382,7 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
     MSGPU_TILE(c, j) {
       dl[c][j] = dvt[c * P + j];  // idle threads and columns past the mesh read the zero pad
       if constexpr (TM) {
+        MSGPU_TM(xcol + 2u * (c * KR + j), 1);
         tm_st1(xcol + 2u * (c * KR + j), dl[c][j]);
       } else {
         xx[c][j] = dl[c][j];
@@ -424,10 +437,12 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
                                  D(c - 1, j - 1), D(c - 1, j), D(c - 1, j + 1), D(c + 1, j - 1), D(c + 1, j),
                                  D(c + 1, j + 1));
           if (maybe_dead(c)) h = col_live[c] ? h : 0.0;
-          if constexpr (TM)
+          if constexpr (TM) {
+            MSGPU_TM(hcol + 2u * (c * KR + j), 1);
             tm_st1(hcol + 2u * (c * KR + j), h);
-          else
+          } else {
             hh[c][j] = h;
+          }
           acc[(c * KR + j) & 3] += dl[c][j] * (shadow(j) ? 0.0 : h);
         }
         dh_part = (acc[0] + acc[1]) + (acc[2] + acc[3]);
@@ -447,6 +462,7 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
           for_each_chunk<E>([&](auto nd, int e0) {
             constexpr int ND = decltype(nd)::value;
             TV<ND> qh;
+            MSGPU_TM(hcol + 2u * e0, ND);
             tm_ld<ND>(hcol + 2u * e0, qh);
             tm_wait<ND>(qh);
 #pragma unroll
@@ -454,6 +470,7 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
               const int c = (e0 + i) / KR, j = (e0 + i) % KR;
               const double go = tv_get<ND>(qh, i) - dvt[c * P + j];
               part += go * (shadow(j) ? 0.0 : go);
+              MSGPU_TM(gcol + 2u * (e0 + i), 1);
               tm_st1(gcol + 2u * (e0 + i), go);
               dl[c][j] = -go;
             }
@@ -495,8 +512,11 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
         for_each_chunk<E>([&](auto nd, int e0) {
           constexpr int ND = decltype(nd)::value;
           TV<ND> qh, qg, qx;
+          MSGPU_TM(hcol + 2u * e0, ND);
           tm_ld<ND>(hcol + 2u * e0, qh);
+          MSGPU_TM(gcol + 2u * e0, ND);
           tm_ld<ND>(gcol + 2u * e0, qg);
+          MSGPU_TM(xcol + 2u * e0, ND);
           tm_ld<ND>(xcol + 2u * e0, qx);
           tm_wait3<ND>(qh, qg, qx);
 #pragma unroll
@@ -505,7 +525,9 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
             const double go = tv_get<ND>(qg, i) + alpha * tv_get<ND>(qh, i);
             const double xo = tv_get<ND>(qx, i) + alpha * dl[c][j];
             acc[(e0 + i) & 3] += go * (shadow(j) ? 0.0 : go);
+            MSGPU_TM(gcol + 2u * (e0 + i), 1);
             tm_st1(gcol + 2u * (e0 + i), go);
+            MSGPU_TM(xcol + 2u * (e0 + i), 1);
             tm_st1(xcol + 2u * (e0 + i), xo);
           }
         });
@@ -551,6 +573,7 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
         for_each_chunk<E>([&](auto nd, int e0) {
           constexpr int ND = decltype(nd)::value;
           TV<ND> qg;
+          MSGPU_TM(gcol + 2u * e0, ND);
           tm_ld<ND>(gcol + 2u * e0, qg);
           tm_wait<ND>(qg);
 #pragma unroll
@@ -578,6 +601,7 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
       for_each_chunk<E>([&](auto nd, int e0) {
         constexpr int ND = decltype(nd)::value;
         TV<ND> qx;
+        MSGPU_TM(xcol + 2u * e0, ND);
         tm_ld<ND>(xcol + 2u * e0, qx);
         tm_wait<ND>(qx);
 #pragma unroll
@@ -609,6 +633,7 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
 #undef MSGPU_RIM
 #undef MSGPU_PUBLISH
 #undef MSGPU_TILE
+#undef MSGPU_TM
   if constexpr (TM) {
     __syncthreads();
     if (warp == 0)
@@ -760,6 +785,12 @@ int launch_stencil_compress(cudaStream_t s, const CgArgs& a, int verify) {
 }
 
 int launch_cg_stencil(cudaStream_t s, const CgArgs& a, int num_sms, const CgSwitches& sw) {
+#ifdef MSGPU_CHECKED
+  if (std::getenv("MSGPU_CHECKED_SELFTEST") != nullptr) {
+    const int one = 1;
+    cudaMemcpyToSymbol(g_checked_selftest, &one, sizeof one);
+  }
+#endif
   StencilPlan p;
   int shape = 0;
   if (!make_plan(a.md, a.dirichlet, p, &shape)) return -1;
