@@ -368,48 +368,63 @@ MSGPU_HOSTDEV void body_face_moments(const VmProgram& prog, int side, const Mesh
 // ---------------------------------------------------------------- K1: gather
 // One thread per (system, node): sums the contributions of the <= 4 cells around the node
 // in the order (cx-1,cy-1), (cx,cy-1), (cx-1,cy), (cx,cy) — no atomics, deterministic.
-MSGPU_HOSTDEV void body_gather(const GatherArgs& a, long long gtid) {
+// body_gather_node: system kl of the chunk, node r.  UNIFORM (GatherArgs::uniform_stiffness): the ten matrix entries
+// and the four weights of a cell are those of cell 0.  Indices inside a system are 32-bit (18 * ncells entries), the
+// per-system offsets 64-bit; the sums keep the order above whatever the template argument.  (Round 2: the kernel
+// was bound by instruction issue - 460 instructions per node, most of them 64-bit index arithmetic and a 64-bit
+// division of the global thread index - not by the 1.5 GB it moves.)
+template <bool UNIFORM>
+MSGPU_HOSTDEV void body_gather_node(const GatherArgs& a, int kl, int r) {
   const MeshDims& md = a.md;
-  const long long t = gtid;
-  if (t >= static_cast<long long>(a.nk) * md.n) return;
-  const int kl = static_cast<int>(t / md.n), r = static_cast<int>(t % md.n);
-  const int ix = r / md.m, iy = r % md.m;
+  const int nc = md.nc, nce = md.ncells;
+  const int ix = r / md.m, iy = r - ix * md.m;
   const int k = a.k0 + kl;
-  const double* cellk = a.cell + static_cast<size_t>(kl) * CELL_STRIDE * md.ncells;
-  const bool uniform = a.uniform_stiffness != 0;
-  auto C = [&](int cx, int cy, int e) -> double {
-    const int c = (uniform && (e < 10 || e >= 14)) ? 0 : cx * md.nc + cy;
-    return MSGPU_LDG(cellk + static_cast<size_t>(e) * md.ncells + c);
+  const double* const cellk = a.cell + static_cast<size_t>(kl) * CELL_STRIDE * nce;
+  const int c11 = ix * nc + iy;  // cell (ix, iy); (ix-1, iy): c11 - nc, (ix, iy-1): c11 - 1, (ix-1, iy-1): c11 - nc - 1
+  // entry e of the cell at offset `off` from c11 (matrix entries and weights of a uniform system: cell 0)
+  auto C = [&](int off, int e) -> double {
+    const int c = (UNIFORM && (e < 10 || e >= 14)) ? 0 : c11 + off;
+    return MSGPU_LDG(cellk + (e * nce + c));
   };
   // the parabolic driver and the L2 projections only want the load vector: the matrix is shared and built
   // on the host, so the ten matrix entries and the four weights of a cell are not even read
   const bool want_matrix = a.diag != nullptr, want_jw = a.jw != nullptr;
+  const bool right_ok = ix < nc, up_ok = iy < nc, down_ok = iy > 0, left_ok = ix > 0;
   double d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, load = 0, jw = 0;
-  for (int dy = -1; dy <= 0; ++dy)
-    for (int dx = -1; dx <= 0; ++dx) {
-      const int cx = ix + dx, cy = iy + dy;
-      if (cx < 0 || cy < 0 || cx >= md.nc || cy >= md.nc) continue;
-      const int v = (ix - cx) + 2 * (iy - cy);
-      if (want_matrix) d0 += C(cx, cy, sym4(v, v));
-      load += C(cx, cy, 10 + v);
-      if (want_jw) jw += C(cx, cy, 14 + v);
-    }
-  const bool right_ok = ix < md.nc, up_ok = iy < md.nc, down_ok = iy > 0, left_ok = ix > 0;
+  // cells (ix-1, iy-1), (ix, iy-1), (ix-1, iy), (ix, iy): this node is their local vertex 3, 2, 1, 0
+  if (left_ok && down_ok) {
+    if (want_matrix) d0 += C(-nc - 1, sym4(3, 3));
+    load += C(-nc - 1, 10 + 3);
+    if (want_jw) jw += C(-nc - 1, 14 + 3);
+  }
+  if (right_ok && down_ok) {
+    if (want_matrix) d0 += C(-1, sym4(2, 2));
+    load += C(-1, 10 + 2);
+    if (want_jw) jw += C(-1, 14 + 2);
+  }
+  if (left_ok && up_ok) {
+    if (want_matrix) d0 += C(-nc, sym4(1, 1));
+    load += C(-nc, 10 + 1);
+    if (want_jw) jw += C(-nc, 14 + 1);
+  }
+  if (right_ok && up_ok) {
+    if (want_matrix) d0 += C(0, sym4(0, 0));
+    load += C(0, 10 + 0);
+    if (want_jw) jw += C(0, 14 + 0);
+  }
   if (want_matrix && up_ok) {  // edge to (ix, iy+1)
-    if (left_ok) d1 += C(ix - 1, iy, 6);   // local (1,3)
-    if (right_ok) d1 += C(ix, iy, 2);      // local (0,2)
+    if (left_ok) d1 += C(-nc, 6);   // local (1,3)
+    if (right_ok) d1 += C(0, 2);    // local (0,2)
   }
   if (want_matrix && right_ok) {  // edge to (ix+1, iy)
-    if (down_ok) d3 += C(ix, iy - 1, 8);   // local (2,3)
-    if (up_ok) d3 += C(ix, iy, 1);         // local (0,1)
-    if (up_ok) d4 += C(ix, iy, 3);         // diagonal to (ix+1, iy+1): local (0,3)
-    if (down_ok) d2 += C(ix, iy - 1, 5);   // diagonal to (ix+1, iy-1): local (1,2)
+    if (down_ok) d3 += C(-1, 8);   // local (2,3)
+    if (up_ok) d3 += C(0, 1);      // local (0,1)
+    if (up_ok) d4 += C(0, 3);      // diagonal to (ix+1, iy+1): local (0,3)
+    if (down_ok) d2 += C(-1, 5);   // diagonal to (ix+1, iy-1): local (1,2)
   }
-  if (a.face != nullptr) {
-    const double* facek = a.face + static_cast<size_t>(kl) * 4 * FACE_STRIDE * md.nc;
-    auto F = [&](int side, int e, int f) -> double {
-      return MSGPU_LDG(facek + (static_cast<size_t>(side) * FACE_STRIDE + e) * md.nc + f);
-    };
+  if (a.face != nullptr && (ix == 0 || ix == md.m - 1 || iy == 0 || iy == md.m - 1)) {
+    const double* facek = a.face + static_cast<size_t>(kl) * 4 * FACE_STRIDE * nc;
+    auto F = [&](int side, int e, int f) -> double { return MSGPU_LDG(facek + ((side * FACE_STRIDE + e) * nc + f)); };
     double* edge = a.edge + static_cast<size_t>(k) * 4 * md.m;
     if (ix == 0 || ix == md.m - 1) {
       const int side = ix == 0 ? 0 : 1;
@@ -429,16 +444,27 @@ MSGPU_HOSTDEV void body_gather(const GatherArgs& a, long long gtid) {
       if (right_ok) load += F(side, 3, ix);
     }
   }
-  if (a.diag != nullptr) {  // parabolic: all systems share one matrix, built once on the host
-    double* dg = a.diag + static_cast<size_t>(k) * NDIAG * md.ld + r;
+  if (want_matrix) {  // parabolic: all systems share one matrix, built once on the host
+    double* dg = a.diag + (static_cast<size_t>(k) * NDIAG * md.ld + r);
     dg[0] = d0;
-    dg[static_cast<size_t>(1) * md.ld] = d1;
-    dg[static_cast<size_t>(2) * md.ld] = d2;
-    dg[static_cast<size_t>(3) * md.ld] = d3;
-    dg[static_cast<size_t>(4) * md.ld] = d4;
+    dg[md.ld] = d1;
+    dg[2 * md.ld] = d2;
+    dg[3 * md.ld] = d3;
+    dg[4 * md.ld] = d4;
   }
   a.b0[static_cast<size_t>(k) * md.n + r] = load;
-  if (a.jw != nullptr) a.jw[static_cast<size_t>(k) * md.n + r] = jw;
+  if (want_jw) a.jw[static_cast<size_t>(k) * md.n + r] = jw;
+}
+
+// global thread index -> (system, node): the sequential CPU harness (tests/native) walks through these
+MSGPU_HOSTDEV void body_gather(const GatherArgs& a, long long gtid) {
+  const MeshDims& md = a.md;
+  if (gtid >= static_cast<long long>(a.nk) * md.n) return;
+  const int kl = static_cast<int>(gtid / md.n), r = static_cast<int>(gtid % md.n);
+  if (a.uniform_stiffness != 0)
+    body_gather_node<true>(a, kl, r);
+  else
+    body_gather_node<false>(a, kl, r);
 }
 
 // ---------------------------------------------------------------- K2: Dirichlet values

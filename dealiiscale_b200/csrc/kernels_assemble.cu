@@ -143,8 +143,11 @@ __global__ void __launch_bounds__(TB) k_face_moments4(const __grid_constant__ Vm
   body_face_moments(prog, side, md, tb, q1d_pt, q1d_wt, k0, nk, has_map, face,
                     static_cast<long long>(blockIdx.x) * TB + threadIdx.x, R + threadIdx.x, TB);
 }
-__global__ void __launch_bounds__(TB) k_gather(GatherArgs a) {
-  body_gather(a, static_cast<long long>(blockIdx.x) * TB + threadIdx.x);
+// blockIdx.x: system of the chunk, blockIdx.y: block of TB nodes (no division of a 64-bit thread index)
+template <bool UNIFORM>
+__global__ void __launch_bounds__(TB) k_gather(const __grid_constant__ GatherArgs a) {
+  const int r = static_cast<int>(blockIdx.y) * TB + static_cast<int>(threadIdx.x);
+  if (r < a.md.n) body_gather_node<UNIFORM>(a, static_cast<int>(blockIdx.x), r);
 }
 __global__ void __launch_bounds__(TB) k_boundary_values(const __grid_constant__ VmProgram prog, MeshDims md, Tables tb,
                                                          int N, double* __restrict__ bv) {
@@ -267,7 +270,11 @@ int launch_face_moments_all(cudaStream_t s, const VmProgram* const prog[4], Mesh
 
 int launch_gather(cudaStream_t s, const GatherArgs& a) {
   if (a.nk == 0) return 0;
-  k_gather<<<blocks_for(static_cast<long long>(a.nk) * a.md.n), TB, 0, s>>>(a);
+  const dim3 grid(static_cast<unsigned>(a.nk), static_cast<unsigned>((a.md.n + TB - 1) / TB));
+  if (a.uniform_stiffness != 0)
+    k_gather<true><<<grid, TB, 0, s>>>(a);
+  else
+    k_gather<false><<<grid, TB, 0, s>>>(a);
   return 1;
 }
 
