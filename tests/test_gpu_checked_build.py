@@ -33,6 +33,7 @@ rng = np.random.default_rng(11)
 xy = rng.uniform(-0.9, 0.9, size=(n_sys, 2))
 problem, cls = (capi.BIO, BioData) if kind == "bio" else (capi.ELLIPTIC, EllipticData)
 ms = MicroSolver(problem, cls(os.path.join(sys.argv[1], "input", prm)), cells, mesh_kind=capi.MESH_SUBDIVIDED)
+ms.max_it = 20000  # the elliptic driver's own limit (1000, micro.cpp:175) is for its coarser meshes
 ms.set_grid_locations(xy)
 ms.setup()
 u = np.sin(xy[:, 0]) * xy[:, 1] + 0.3
