@@ -69,6 +69,17 @@ CASES = [
 ]
 
 
+def _checked_lib():
+    """The library normally travels with the tree (__graft_entry__.build()); nvcc is on the GPU boxes too."""
+    lib = os.path.join(ROOT, "dealiiscale_b200", "_build", "libmsgpu_checked.so")
+    if not os.path.exists(lib):
+        sys.path.insert(0, ROOT)
+        from dealiiscale_b200 import build as b
+        b.build_checked()
+    assert os.path.exists(lib)
+    return lib
+
+
 def _run(which, kind, prm, cells, n_sys, env, out):
     e = dict(os.environ)
     for k in ("MSGPU_CG_STENCIL", "MSGPU_STENCIL_TMEM", "MSGPU_STENCIL_VARIANT"):
@@ -83,8 +94,7 @@ def _run(which, kind, prm, cells, n_sys, env, out):
 
 @pytest.mark.parametrize("kind,prm,cells,n_sys,env,variant", CASES)
 def test_no_access_leaves_its_window(kind, prm, cells, n_sys, env, variant, tmp_path):
-    lib = os.path.join(ROOT, "dealiiscale_b200", "_build", "libmsgpu_checked.so")
-    assert os.path.exists(lib), "build it with `python -m dealiiscale_b200.build` (build_checked)"
+    lib = _checked_lib()
     chk = _run("checked", kind, prm, cells, n_sys, env, str(tmp_path / "checked.npz"))
     ref = _run("product", kind, prm, cells, n_sys, env, str(tmp_path / "product.npz"))
     assert int(ref["variant"]) & 0xff == variant or int(ref["variant"]) >> 8 == variant, int(ref["variant"])
@@ -99,8 +109,7 @@ def test_no_access_leaves_its_window(kind, prm, cells, n_sys, env, variant, tmp_
 def test_the_checks_fire(tmp_path):
     """The trap path itself: a checked build must fail loudly when a window is violated.  MSGPU_CHECKED_SELFTEST makes
     k_cg_stencil read one double in front of its shared-memory window."""
-    lib = os.path.join(ROOT, "dealiiscale_b200", "_build", "libmsgpu_checked.so")
-    assert os.path.exists(lib)
+    lib = _checked_lib()
     e = dict(os.environ)
     e["MSGPU_CHECKED_SELFTEST"] = "1"
     res = subprocess.run([sys.executable, "-c", RUNNER, ROOT, "checked", "bio", "biocase.prm", "64", "2",
