@@ -121,7 +121,7 @@ struct CgSwitches {
   int stencil = 1;         // MSGPU_CG_STENCIL=0: never take the class-compressed kernel
   int stencil_tmem = 1;    // MSGPU_STENCIL_TMEM=0: its all-register variant (one system per SM)
   int stencil_ctas = 0;    // MSGPU_STENCIL_CTAS=n: at most n CTAs of it per SM
-  int stencil_variant = 0; // MSGPU_STENCIL_VARIANT=1: masks for any overlap / dead columns even where the counts are known (A/B)
+  int stencil_variant = 0; // MSGPU_STENCIL_VARIANT=1: masks for any overlap / dead columns even where the counts are known; 2: x updated between the reductions (A/B)
   int force_global = 0;    // MSGPU_CG_VARIANT=global: the streaming kernel
   int wide = 0;            // MSGPU_CG_WIDE=1: 1024 threads x 5 rows instead of 512 x 9 (strided kernel)
   int strided = 0;         // MSGPU_CG_STRIDED=1: strided row ownership

@@ -167,6 +167,21 @@ __device__ __forceinline__ void tm_wait(TV<ND>& q) {
   }
 }
 template <int ND>
+__device__ __forceinline__ void tm_wait2(TV<ND>& a, TV<ND>& b) {
+  if constexpr (ND == 4) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(a.r[0]), "+r"(a.r[1]), "+r"(a.r[2]), "+r"(a.r[3]), "+r"(a.r[4]), "+r"(a.r[5]), "+r"(a.r[6]),
+                   "+r"(a.r[7]), "+r"(b.r[0]), "+r"(b.r[1]), "+r"(b.r[2]), "+r"(b.r[3]), "+r"(b.r[4]), "+r"(b.r[5]),
+                   "+r"(b.r[6]), "+r"(b.r[7]));
+  } else if constexpr (ND == 2) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(a.r[0]), "+r"(a.r[1]), "+r"(a.r[2]), "+r"(a.r[3]), "+r"(b.r[0]), "+r"(b.r[1]), "+r"(b.r[2]),
+                   "+r"(b.r[3]));
+  } else {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : "+r"(a.r[0]), "+r"(a.r[1]), "+r"(b.r[0]), "+r"(b.r[1]));
+  }
+}
+template <int ND>
 __device__ __forceinline__ void tm_wait3(TV<ND>& a, TV<ND>& b, TV<ND>& c) {
   if constexpr (ND == 4) {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n"
@@ -246,7 +261,14 @@ __device__ __forceinline__ double stencil_row(double cself, double cv, double ch
 // (Measured and dropped: the couplings of the first and last row of a tile read from the class table in shared memory
 // at their place of use instead of sitting in 16 registers: 8.63 against 8.28 ms; all of g loaded from tensor memory
 // at once in the direction update instead of four values at a time: 8.37 against 8.28 ms.)
-template <bool TM, int W, int KR, int OVN, int DCN>
+// XL (tensor-memory variant): x += alpha d is done in the direction phase behind the second reduction - where the
+// loads of g leave the FP64 pipe idle anyway - instead of in the update phase between the two reductions of a step
+// (8.27 -> 8.18 ms on the bench workload, the same bits: the operations and their operands do not change).  A system
+// that leaves the loop right after its last update adds the pending alpha d when it writes x back.
+// (Measured and dropped on top of it: the first four values of g fetched while the block sum of d.h is formed and kept
+// in registers through the second reduction, the first four of x fetched during the latter: 8.36 ms.)
+// (Requesting the first values of h and g before alpha = gh / d.h is formed changes nothing: 8.19 ms.)
+template <bool TM, int W, int KR, int OVN, int DCN, bool XL = TM>
 __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
     k_cg_stencil(const __grid_constant__ CgArgs a, const __grid_constant__ StencilPlan p) {
   if (a.gate != nullptr && ((*a.gate == 0) != (a.gate_run_if_zero != 0))) return;  // the other kernel does the work
@@ -393,7 +415,8 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
     // ones are CG steps: one place of use for the SpMV.
     bool start = true, ok = false;
     int it = 0;
-    double res = 0.0, gh = 0.0, rgh = 0.0;
+    double res = 0.0, gh = 0.0, rgh = 0.0, alpha = 0.0;
+    [[maybe_unused]] bool x_pending = false;  // XL: the x update of the step just taken has not been done yet
 #ifdef MSGPU_STENCIL_STAMPS
     long long st_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, st_c = clock64();
 #define MSGPU_STAMP(i)                                    \
@@ -501,36 +524,48 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
       if (dh == 1.2345e-300) st_t[7] += 1;
 #endif
       MSGPU_STAMP(2)  // first reduction
-      const double alpha = gh / dh;
+      alpha = gh / dh;
 #ifdef MSGPU_STENCIL_STAMPS
       if (alpha == 1.2345e-300) st_t[7] += 1;
 #endif
       MSGPU_STAMP(3)  // alpha
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
       if constexpr (TM) {
-        tm_st_wait();  // h of this step (and x, g of the last one) have landed
-        for_each_chunk<E>([&](auto nd, int e0) {
+        auto update = [&](auto nd, int e0, auto& qh, auto& qg, auto& qx) {
+          constexpr int ND = decltype(nd)::value;
+#pragma unroll
+          for (int i = 0; i < ND; ++i) {
+            const int c = (e0 + i) / KR, j = (e0 + i) % KR;
+            const double go = tv_get<ND>(qg, i) + alpha * tv_get<ND>(qh, i);
+            acc[(e0 + i) & 3] += go * (shadow(j) ? 0.0 : go);
+            MSGPU_TM(gcol + 2u * (e0 + i), 1);
+            tm_st1(gcol + 2u * (e0 + i), go);
+            if constexpr (!XL) {
+              const double xo = tv_get<ND>(qx, i) + alpha * dl[c][j];
+              MSGPU_TM(xcol + 2u * (e0 + i), 1);
+              tm_st1(xcol + 2u * (e0 + i), xo);
+            }
+          }
+        };
+        auto chunk = [&](auto nd, int e0) {
           constexpr int ND = decltype(nd)::value;
           TV<ND> qh, qg, qx;
           MSGPU_TM(hcol + 2u * e0, ND);
           tm_ld<ND>(hcol + 2u * e0, qh);
           MSGPU_TM(gcol + 2u * e0, ND);
           tm_ld<ND>(gcol + 2u * e0, qg);
-          MSGPU_TM(xcol + 2u * e0, ND);
-          tm_ld<ND>(xcol + 2u * e0, qx);
-          tm_wait3<ND>(qh, qg, qx);
-#pragma unroll
-          for (int i = 0; i < ND; ++i) {
-            const int c = (e0 + i) / KR, j = (e0 + i) % KR;
-            const double go = tv_get<ND>(qg, i) + alpha * tv_get<ND>(qh, i);
-            const double xo = tv_get<ND>(qx, i) + alpha * dl[c][j];
-            acc[(e0 + i) & 3] += go * (shadow(j) ? 0.0 : go);
-            MSGPU_TM(gcol + 2u * (e0 + i), 1);
-            tm_st1(gcol + 2u * (e0 + i), go);
-            MSGPU_TM(xcol + 2u * (e0 + i), 1);
-            tm_st1(xcol + 2u * (e0 + i), xo);
+          if constexpr (!XL) {
+            MSGPU_TM(xcol + 2u * e0, ND);
+            tm_ld<ND>(xcol + 2u * e0, qx);
+            tm_wait3<ND>(qh, qg, qx);
+          } else {
+            tm_wait2<ND>(qh, qg);
           }
-        });
+          update(nd, e0, qh, qg, qx);
+        };
+        tm_st_wait();  // h of this step (and x, g of the last one) have landed
+        for_each_chunk<E>(chunk);
+        if constexpr (XL) x_pending = true;
       } else {
         MSGPU_TILE(c, j) {
           xx[c][j] += alpha * dl[c][j];
@@ -572,17 +607,29 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
         tm_st_wait();
         for_each_chunk<E>([&](auto nd, int e0) {
           constexpr int ND = decltype(nd)::value;
-          TV<ND> qg;
+          TV<ND> qg, qx;
           MSGPU_TM(gcol + 2u * e0, ND);
           tm_ld<ND>(gcol + 2u * e0, qg);
-          tm_wait<ND>(qg);
+          if constexpr (XL) {
+            MSGPU_TM(xcol + 2u * e0, ND);
+            tm_ld<ND>(xcol + 2u * e0, qx);
+            tm_wait2<ND>(qg, qx);
+          } else {
+            tm_wait<ND>(qg);
+          }
 #pragma unroll
           for (int i = 0; i < ND; ++i) {
             const int c = (e0 + i) / KR, j = (e0 + i) % KR;
+            if constexpr (XL) {  // x += alpha d with the direction of the step just taken, before it is replaced
+              const double xo = tv_get<ND>(qx, i) + alpha * dl[c][j];
+              MSGPU_TM(xcol + 2u * (e0 + i), 1);
+              tm_st1(xcol + 2u * (e0 + i), xo);
+            }
             dl[c][j] = beta * dl[c][j] - tv_get<ND>(qg, i);
             if (MSGPU_RIM(c, j) && col_live[c] && !shadow(j)) dvt[c * P + j] = dl[c][j];
           }
         });
+        if constexpr (XL) x_pending = false;
       } else {
         MSGPU_TILE(c, j) dl[c][j] = beta * dl[c][j] - gg[c][j];
         MSGPU_PUBLISH_RIM(dl);
@@ -607,7 +654,9 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
 #pragma unroll
         for (int i = 0; i < ND; ++i) {
           const int c = (e0 + i) / KR, j = (e0 + i) % KR;
-          if (col_live[c] && !shadow(j)) dvt[c * P + j] = tv_get<ND>(qx, i);
+          double xv = tv_get<ND>(qx, i);
+          if constexpr (XL) xv = x_pending ? xv + alpha * dl[c][j] : xv;  // the loop was left before this update
+          if (col_live[c] && !shadow(j)) dvt[c * P + j] = xv;
         }
       });
     } else {
@@ -732,10 +781,10 @@ __global__ void __launch_bounds__(128) k_stencil_compress(MeshDims md, int nsys,
   }
 }
 
-template <bool TM, int W, int KR, int OVN, int DCN>
+template <bool TM, int W, int KR, int OVN, int DCN, bool XL = TM>
 int launch_plan(cudaStream_t s, const CgArgs& a, const StencilPlan& p, int num_sms, const CgSwitches& sw) {
   const size_t smem = plan_smem_bytes(p);
-  auto kern = k_cg_stencil<TM, W, KR, OVN, DCN>;
+  auto kern = k_cg_stencil<TM, W, KR, OVN, DCN, XL>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
     cudaGetLastError();
     return -1;
@@ -799,6 +848,8 @@ int launch_cg_stencil(cudaStream_t s, const CgArgs& a, int num_sms, const CgSwit
   if (shape == 0)
     return use_tm ? launch_plan<true, 3, 7, 0, 0>(s, a, p, num_sms, sw) : launch_plan<false, 3, 7, 0, 0>(s, a, p, num_sms, sw);
   // 65 x 65 nodes (64 x 64 cells, Robin / Neumann boundaries): one shared row, one tile column past the mesh
+  if (use_tm && p.ov == 1 && dc == 1 && sw.stencil_variant == 2)  // A/B: x updated between the two reductions
+    return launch_plan<true, 3, 6, 1, 1, false>(s, a, p, num_sms, sw);
   if (use_tm && p.ov == 1 && dc == 1 && sw.stencil_variant != 1) return launch_plan<true, 3, 6, 1, 1>(s, a, p, num_sms, sw);
   return use_tm ? launch_plan<true, 3, 6, -1, -1>(s, a, p, num_sms, sw) : launch_plan<false, 3, 6, -1, -1>(s, a, p, num_sms, sw);
 }

@@ -374,9 +374,15 @@ int parabolic_assemble(msgpu_ctx* ctx, double dt, double t) {
   mp.jac_depends_on_y = 0;
   for (int k0 = 0; k0 < N; k0 += ctx->chunk) {
     const int nk = std::min(ctx->chunk, N - k0);
-    ctx->launches += launch_cell_moments(ctx->stream, mp, md, tb, ctx->d_qtab,
-                                         ctx->d_qtab + static_cast<size_t>(md.q) * md.q * QTAB_STRIDE, k0, nk, 1.0,
-                                         ctx->d_cell, ctx->d_flags + FLAG_JACOBIAN);
+    int launched = -1;
+    if (ctx->jit_kernels)
+      launched = launch_cell_moments_jit(ctx->stream, ctx->jit_moments, md, tb, k0, nk, 1.0, ctx->d_cell,
+                                         ctx->d_flags + FLAG_JACOBIAN);
+    if (launched < 0)
+      launched = launch_cell_moments(ctx->stream, mp, md, tb, ctx->d_qtab,
+                                     ctx->d_qtab + static_cast<size_t>(md.q) * md.q * QTAB_STRIDE, k0, nk, 1.0,
+                                     ctx->d_cell, ctx->d_flags + FLAG_JACOBIAN);
+    ctx->launches += launched;
     const VmProgram* faces[4];
     for (int s = 0; s < 4; ++s) faces[s] = &ps.point_program(ctx->pp.prog_face[s]);
     ctx->launches += launch_face_moments_all(ctx->stream, faces, md, tb, ctx->d_q1pt, ctx->d_q1wt, k0, nk, 0, ctx->d_face);

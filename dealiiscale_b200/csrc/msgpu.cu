@@ -336,14 +336,14 @@ int msgpu_setup(msgpu_ctx* ctx) {
   const std::vector<double> q1d = build_q1d(md.q, pt, wt);
   if (upload_constant_tables(md.q, qtab.data(), qsum.data(), q1d.data()))
     return fail(ctx, MSGPU_ERR_CUDA, "cannot upload the quadrature tables to constant memory");
-  // Specialise the cell-moment kernel for this problem's expressions (elliptic and bio assemble
-  // every cycle).  Any failure leaves the interpreter kernels in charge and is kept in jit_log.
+  // Specialise the cell-moment kernel for this problem's expressions (elliptic and bio assemble every cycle, the
+  // parabolic driver every time step).  Any failure leaves the interpreter kernels in charge and is kept in jit_log.
   ctx->jit_kernels = 0;
   ctx->jit_errors_ready = 0;
   ctx->jit_log.clear();
   {
     const char* jit_env = std::getenv("MSGPU_JIT");
-    if (ctx->desc.problem != MSGPU_PARABOLIC && !(jit_env && jit_env[0] == '0')) {
+    if (!(jit_env && jit_env[0] == '0')) {  // parabolic: prog_vol = prog_vol_G, no mapping, QGauss(2)
       const ProgramSet& ps = ctx->pp.ps;
       MomentPrograms mp;
       mp.full = &ps.point_program(ctx->pp.prog_vol);

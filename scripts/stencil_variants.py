@@ -1,5 +1,6 @@
 """A/B of code-generation variants of k_cg_stencil on the bench workload (4225 bio systems of 64 x 64 cells):
-MSGPU_STENCIL_VARIANT = 0 | 1 (masks with exact counts) | 2 (rim couplings from shared memory) | 3 (both).
+MSGPU_STENCIL_VARIANT = 0 (default) | 1 (masks on every row / column that could be shared or dead) | 2 (x updated
+between the two reductions of a step instead of behind the second one).
 
     python scripts/stencil_variants.py [variants ...]
 """

@@ -116,3 +116,40 @@ def test_specialised_error_kernel_matches_interpreter(problem, prm, cells):
     # arithmetic may be contracted differently by nvcc and NVRTC
     np.testing.assert_allclose(out[True][0], out[False][0], rtol=1e-9)
     np.testing.assert_allclose(out[True][1], out[False][1], rtol=1e-6)
+
+
+@pytest.mark.parametrize("prm", ["linear_time.prm", "full_nonlinear.prm"])
+def test_parabolic_time_steps_with_and_without_the_specialised_kernel(prm):
+    """RhoSolver::assemble_system (rho_solver.cpp:134-147) integrates the source with QGauss(2) at every time step; the
+    NVRTC kernel and the interpreter must give the same right-hand sides and the same steps."""
+    from dealiiscale_b200 import capi
+    from dealiiscale_b200.micro import MicroSolver
+    from dealiiscale_b200.prm import TwoPressureData
+
+    g = np.linspace(-0.9, 0.8, 3)
+    xy = np.array([(a, b) for b in g for a in g])
+    pi = 1.0 + 0.5 * xy[:, 0] - 0.25 * xy[:, 1]
+    out = {}
+    old = os.environ.get("MSGPU_JIT")
+    try:
+        for jit in (False, True):
+            os.environ["MSGPU_JIT"] = "1" if jit else "0"
+            ms = MicroSolver(capi.PARABOLIC, TwoPressureData(os.path.join(INPUT, prm)), 16)
+            ms.set_grid_locations(xy)
+            ms.setup()
+            assert ms.stats()["jit_kernels"] >= (1 if jit else 0), ms.jit_log()
+            if not jit:
+                assert ms.stats()["jit_kernels"] == 0
+            ms.set_macro_solution(pi)
+            its = [ms.iterate(0.05, 0.05 * (i + 1)).copy() for i in range(3)]
+            out[jit] = (np.stack(its), ms.righthandsides(), ms.solutions())
+            ms.close()
+    finally:
+        if old is None:
+            os.environ.pop("MSGPU_JIT", None)
+        else:
+            os.environ["MSGPU_JIT"] = old
+    (its_i, b_i, x_i), (its_j, b_j, x_j) = out[False], out[True]
+    assert np.abs(b_j - b_i).max() <= 4e-15 * max(np.abs(b_i).max(), 1e-300)
+    assert np.abs(x_j - x_i).max() <= 1e-12 * max(np.abs(x_i).max(), 1e-300)
+    assert np.array_equal(its_i, its_j)
