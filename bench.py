@@ -653,12 +653,13 @@ def main():
             peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        traffic, traffic_src = None, None
+        traffic, traffic_src, pipe_ncu = None, None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if tj.get("cg_variant") == int(st["cg_variant"]):
                 traffic, traffic_src = tj.get("cg_bytes_per_launch"), tj.get("source")
+                pipe_ncu = tj.get("fp64_pipe_active_pct")  # same committed capture: not measured in this run
         achieved = cg_bytes / (cg_ms * 1e-3) / 1e9
         value = n_total * n * args.steps / t_dev
         e2e_value = n_total * n * args.steps / t_e2e
@@ -681,6 +682,7 @@ def main():
                 "bound": "fp64/on-chip", "kernel": CG_KERNEL_NAMES.get(int(st["cg_variant"]), "batched CG"),
                 "achieved": fp64["achieved"], "peak": fp64["peak"], "unit": "TFLOP/s", "frac": fp64["frac"],
                 "traffic": traffic, "traffic_source": traffic_src,
+                "fp64_pipe_active_pct_ncu": pipe_ncu,
                 "peak_source": fp64["peak_source"], "flops_model": fp64["flops_model"],
                 "algorithmic_flops_per_launch": cg_flops,
                 "kernel_ms_per_launch": cg_ms,
