@@ -267,7 +267,8 @@ __device__ __forceinline__ double stencil_row(double cself, double cv, double ch
 // that leaves the loop right after its last update adds the pending alpha d when it writes x back.
 // (Measured and dropped on top of it: the first four values of g fetched while the block sum of d.h is formed and kept
 // in registers through the second reduction, the first four of x fetched during the latter: 8.36 ms.)
-// (Requesting the first values of h and g before alpha = gh / d.h is formed changes nothing: 8.19 ms.)
+// (Requesting the first values of h and g before alpha = gh / d.h is formed changes nothing: 8.19 ms; g and x written
+// back two doubles per tcgen05.st: 8.37 ms, the pairs cost register moves again.)
 template <bool TM, int W, int KR, int OVN, int DCN, bool XL = TM>
 __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
     k_cg_stencil(const __grid_constant__ CgArgs a, const __grid_constant__ StencilPlan p) {
