@@ -29,7 +29,7 @@ EXPORTED = [
     "msgpu_macro_set_solution", "msgpu_macro_get_solution", "msgpu_macro_solve", "msgpu_comm_p2p_export",
     "msgpu_comm_p2p_attach", "msgpu_set_exact_solution", "msgpu_comm_allgather", "msgpu_comm_p2p_detach",
     "msgpu_reload_switches", "msgpu_macro_set_product_load", "msgpu_norm_setup", "msgpu_norm_of_values",
-    "msgpu_norm_of_residuals", "msgpu_norm_of_errors",
+    "msgpu_norm_of_residuals", "msgpu_norm_of_errors", "msgpu_assemble_begin",
 ]
 
 
@@ -84,6 +84,7 @@ def load():
     lib.msgpu_num_dofs.argtypes = [vp]
     lib.msgpu_set_macro_solution.argtypes = [vp, dp, dp]
     lib.msgpu_assemble.argtypes = [vp]
+    lib.msgpu_assemble_begin.argtypes = [vp]
     lib.msgpu_solve.argtypes = [vp, C.c_double, C.c_int, C.c_int, ip, dp]
     lib.msgpu_time_step.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, ip]
     lib.msgpu_coupling.argtypes = [vp, dp, dp]

@@ -107,6 +107,11 @@ struct msgpu_ctx {
   // depend on the macro solution, so after the first msgpu_assemble of a set-up only the right-hand sides are
   // refreshed.  Off by default: the reference re-assembles in every cycle and so does the default path.
   int reuse_assembly = 0, assembly_cached = 0;
+  // msgpu_assemble_begin: the macro-independent part of the (bio) assembly on a second stream, beside the macro solve
+  int overlap_assembly = 1;          // MSGPU_OVERLAP_ASSEMBLY=0: msgpu_assemble_begin does nothing
+  int pre_assembly_in_flight = 0;    // launched on aux_stream, not yet joined by msgpu_assemble
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_pre = nullptr;
   double tables_time = 0.0;
   std::vector<int> h_iters;
   long long cg_iterations_total = 0;

@@ -75,16 +75,17 @@ void free_all(msgpu_ctx* ctx) {
 struct PhaseTimer {
   msgpu_ctx* ctx;
   int phase;
+  cudaStream_t s;
   cudaEvent_t a = nullptr, b = nullptr;
-  PhaseTimer(msgpu_ctx* c, int ph) : ctx(c), phase(ph) {
+  PhaseTimer(msgpu_ctx* c, int ph, cudaStream_t stream = nullptr) : ctx(c), phase(ph), s(stream ? stream : c->stream) {
     if (!ctx->timing) return;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
-    cudaEventRecord(a, ctx->stream);
+    cudaEventRecord(a, s);
   }
   ~PhaseTimer() {
     if (!ctx->timing) return;
-    cudaEventRecord(b, ctx->stream);
+    cudaEventRecord(b, s);
     ctx->pending.push_back({phase, a, b});
   }
 };
@@ -194,6 +195,8 @@ int msgpu_create(msgpu_ctx** out, const msgpu_desc* desc) {
   {
     const char* e = std::getenv("MSGPU_REUSE_ASSEMBLY");
     ctx->reuse_assembly = e && e[0] == '1';
+    const char* o = std::getenv("MSGPU_OVERLAP_ASSEMBLY");
+    ctx->overlap_assembly = !(o && o[0] == '0');
   }
   try {
     ctx->ref_to_internal = reference_numbering(desc->mesh_kind, desc->cells_per_axis);
@@ -206,9 +209,19 @@ int msgpu_create(msgpu_ctx** out, const msgpu_desc* desc) {
   return MSGPU_OK;
 }
 
+// A pre-assembly that nobody has joined yet must not outlive the buffers or the inputs it works on.
+static void retire_pre_assembly(msgpu_ctx* ctx) {
+  if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+  ctx->pre_assembly_in_flight = 0;
+}
+
 void msgpu_destroy(msgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  retire_pre_assembly(ctx);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
+  if (ctx->ev_pre) cudaEventDestroy(ctx->ev_pre);
   cudaStreamSynchronize(ctx->stream);
   drain_timers(ctx);
   comm_destroy(ctx);
@@ -243,6 +256,7 @@ int msgpu_synchronize(msgpu_ctx* ctx) {
 }
 
 int msgpu_set_grid_locations(msgpu_ctx* ctx, const double* xy, int n_grids) {
+  if (ctx) retire_pre_assembly(ctx);
   if (!ctx || !xy || n_grids < 0) return MSGPU_ERR_INVALID;
   ctx->N = n_grids;
   ctx->xy.assign(xy, xy + 2 * static_cast<size_t>(n_grids));
@@ -252,6 +266,7 @@ int msgpu_set_grid_locations(msgpu_ctx* ctx, const double* xy, int n_grids) {
 
 int msgpu_set_function(msgpu_ctx* ctx, int slot, const char* expr, const char* const* const_names,
                        const double* const_values, int n_consts, int time_dependent) {
+  if (ctx) retire_pre_assembly(ctx);
   if (!ctx || slot < 0 || slot >= MSGPU_FN_COUNT || !expr || n_consts < 0) return MSGPU_ERR_INVALID;
   FnDef& f = ctx->fn[slot];
   f.set = true;
@@ -296,6 +311,7 @@ int msgpu_set_function(msgpu_ctx* ctx, int slot, const char* expr, const char* c
 
 int msgpu_set_scalars(msgpu_ctx* ctx, const double* values, int n) {
   if (!ctx || !values || n < 0 || n > MSGPU_MAX_SCALARS) return MSGPU_ERR_INVALID;
+  retire_pre_assembly(ctx);
   for (int i = 0; i < n; ++i) ctx->scalars[i] = values[i];
   ctx->n_scalars = n;
   ctx->stencil_hint = 0;  // the Robin terms of the matrices change with the scalars
@@ -305,6 +321,7 @@ int msgpu_set_scalars(msgpu_ctx* ctx, const double* values, int n) {
 
 int msgpu_setup(msgpu_ctx* ctx) {
   if (!ctx) return MSGPU_ERR_INVALID;
+  retire_pre_assembly(ctx);
   if (ctx->N <= 0) return fail(ctx, MSGPU_ERR_INVALID, "set_grid_locations must be called before setup");
   CK(cudaSetDevice(ctx->device));
   const int prob = ctx->desc.problem;
@@ -473,6 +490,91 @@ int msgpu_set_macro_solution(msgpu_ctx* ctx, const double* u, const double* w) {
   return MSGPU_OK;
 }
 
+// The part of the assembly that does not depend on the macro solution - cell and face moments, the gather into
+// matrices, loads and weights - for all systems, on stream `st`.
+static int assemble_macro_independent(msgpu_ctx* ctx, cudaStream_t st) {
+  const MeshDims& md = ctx->md;
+  const ProgramSet& ps = ctx->pp.ps;
+  const int prob = ctx->desc.problem;
+  const Tables tb = tables_of(ctx);
+  const double d2 = prob == MSGPU_BIO ? ctx->scalars[4] : 1.0;
+  for (int k0 = 0; k0 < ctx->N; k0 += ctx->chunk) {
+    const int nk = std::min(ctx->chunk, ctx->N - k0);
+    {
+      PhaseTimer pt(ctx, PH_MOMENTS, st);
+      MomentPrograms mp;
+      mp.full = &ps.point_program(ctx->pp.prog_vol);
+      mp.F = ctx->pp.prog_vol_F >= 0 ? &ps.point_program(ctx->pp.prog_vol_F) : mp.full;
+      mp.G = &ps.point_program(ctx->pp.prog_vol_G);
+      mp.has_map = ctx->pp.has_map;
+      mp.jac_depends_on_y = ctx->pp.jac_depends_on_y;
+      int launched = -1;
+      if (ctx->jit_kernels)
+        launched = launch_cell_moments_jit(st, ctx->jit_moments, md, tb, k0, nk, d2, ctx->d_cell,
+                                           ctx->d_flags + FLAG_JACOBIAN);
+      if (launched < 0)
+        launched = launch_cell_moments(st, mp, md, tb, ctx->d_qtab,
+                                       ctx->d_qtab + static_cast<size_t>(md.q) * md.q * QTAB_STRIDE, k0, nk, d2,
+                                       ctx->d_cell, ctx->d_flags + FLAG_JACOBIAN);
+      ctx->launches += launched;
+      if (prob == MSGPU_BIO) {
+        const VmProgram* faces[4];
+        for (int s = 0; s < 4; ++s) faces[s] = &ps.point_program(ctx->pp.prog_face[s]);
+        ctx->launches += launch_face_moments_all(st, faces, md, tb, ctx->d_q1pt, ctx->d_q1wt, k0, nk,
+                                                 ctx->pp.has_map, ctx->d_face);
+      }
+    }
+    {
+      PhaseTimer pt(ctx, PH_GATHER, st);
+      GatherArgs g{};
+      g.uniform_stiffness = (!ctx->pp.has_map || !ctx->pp.jac_depends_on_y) ? 1 : 0;
+      g.md = md;
+      g.problem = prob;
+      g.k0 = k0;
+      g.nk = nk;
+      g.cell = ctx->d_cell;
+      g.face = prob == MSGPU_BIO ? ctx->d_face : nullptr;
+      g.robin_left = prob == MSGPU_BIO ? ctx->scalars[1] : 0.0;
+      g.robin_right = prob == MSGPU_BIO ? ctx->scalars[3] : 0.0;
+      g.diag = ctx->d_diag;
+      g.b0 = ctx->d_b0;
+      g.jw = ctx->d_jw;
+      g.edge = ctx->d_edge;
+      ctx->launches += launch_gather(st, g);
+    }
+  }
+  return MSGPU_OK;
+}
+
+int msgpu_assemble_begin(msgpu_ctx* ctx) {
+  if (!ctx || !ctx->setup_done) return MSGPU_ERR_INVALID;
+  // bio only (the elliptic right-hand side and the parabolic step are one pass each), and not when the assembly is
+  // cached anyway
+  if (ctx->desc.problem != MSGPU_BIO || !ctx->overlap_assembly || ctx->pre_assembly_in_flight) return MSGPU_OK;
+  if (ctx->reuse_assembly && ctx->assembly_cached) return MSGPU_OK;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->tables_valid) {
+    const int rc = build_tables(ctx, 0.0);
+    if (rc) return rc;
+  }
+  if (!ctx->aux_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming));
+  }
+  // behind everything the main stream has been given so far (the last solve, coupling, stop test read what is
+  // rewritten now), beside whatever it is given next
+  CK(cudaEventRecord(ctx->ev_main, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_main, 0));
+  const int rc = assemble_macro_independent(ctx, ctx->aux_stream);
+  if (rc) return rc;
+  CKVM();
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev_pre, ctx->aux_stream));
+  ctx->pre_assembly_in_flight = 1;
+  return MSGPU_OK;
+}
+
 int msgpu_assemble(msgpu_ctx* ctx) {
   if (!ctx || !ctx->setup_done) return MSGPU_ERR_INVALID;
   if (ctx->desc.problem == MSGPU_PARABOLIC)
@@ -490,50 +592,13 @@ int msgpu_assemble(msgpu_ctx* ctx) {
   // (bio only: the elliptic right-hand side eliminates the Dirichlet columns from the UNMASKED matrix, which a
   // second pass no longer has)
   const bool reuse = ctx->reuse_assembly && ctx->assembly_cached && prob == MSGPU_BIO;
-  for (int k0 = 0; k0 < ctx->N && !reuse; k0 += ctx->chunk) {
-    const int nk = std::min(ctx->chunk, ctx->N - k0);
-    {
-      PhaseTimer pt(ctx, PH_MOMENTS);
-      MomentPrograms mp;
-      mp.full = &ps.point_program(ctx->pp.prog_vol);
-      mp.F = ctx->pp.prog_vol_F >= 0 ? &ps.point_program(ctx->pp.prog_vol_F) : mp.full;
-      mp.G = &ps.point_program(ctx->pp.prog_vol_G);
-      mp.has_map = ctx->pp.has_map;
-      mp.jac_depends_on_y = ctx->pp.jac_depends_on_y;
-      int launched = -1;
-      if (ctx->jit_kernels)
-        launched = launch_cell_moments_jit(ctx->stream, ctx->jit_moments, md, tb, k0, nk, d2, ctx->d_cell,
-                                           ctx->d_flags + FLAG_JACOBIAN);
-      if (launched < 0)
-        launched = launch_cell_moments(ctx->stream, mp, md, tb, ctx->d_qtab,
-                                       ctx->d_qtab + static_cast<size_t>(md.q) * md.q * QTAB_STRIDE, k0, nk, d2,
-                                       ctx->d_cell, ctx->d_flags + FLAG_JACOBIAN);
-      ctx->launches += launched;
-      if (prob == MSGPU_BIO) {
-        const VmProgram* faces[4];
-        for (int s = 0; s < 4; ++s) faces[s] = &ps.point_program(ctx->pp.prog_face[s]);
-        ctx->launches += launch_face_moments_all(ctx->stream, faces, md, tb, ctx->d_q1pt, ctx->d_q1wt, k0, nk,
-                                                 ctx->pp.has_map, ctx->d_face);
-      }
-    }
-    {
-      PhaseTimer pt(ctx, PH_GATHER);
-      GatherArgs g{};
-      g.uniform_stiffness = (!ctx->pp.has_map || !ctx->pp.jac_depends_on_y) ? 1 : 0;
-      g.md = md;
-      g.problem = prob;
-      g.k0 = k0;
-      g.nk = nk;
-      g.cell = ctx->d_cell;
-      g.face = prob == MSGPU_BIO ? ctx->d_face : nullptr;
-      g.robin_left = prob == MSGPU_BIO ? ctx->scalars[1] : 0.0;
-      g.robin_right = prob == MSGPU_BIO ? ctx->scalars[3] : 0.0;
-      g.diag = ctx->d_diag;
-      g.b0 = ctx->d_b0;
-      g.jw = ctx->d_jw;
-      g.edge = ctx->d_edge;
-      ctx->launches += launch_gather(ctx->stream, g);
-    }
+  if (ctx->pre_assembly_in_flight) {
+    // msgpu_assemble_begin has put the macro-independent part on the auxiliary stream: join it here
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0));
+    ctx->pre_assembly_in_flight = 0;
+  } else if (!reuse) {
+    const int rc = assemble_macro_independent(ctx, ctx->stream);
+    if (rc) return rc;
   }
   {
     PhaseTimer pt(ctx, PH_GATHER);

@@ -146,6 +146,9 @@ class MacroSolver {
       const bool fine = tm && tm[0] == '2';
       const auto t0 = std::chrono::steady_clock::now();
       compute_microscopic_contribution();  // integrals stay on the device; host copies are for the records
+      // the matrices, loads and weights of the micro systems do not depend on what is solved for next: their assembly
+      // runs on a second stream beside the macro solve (the reference does one after the other, manager.cpp:65-68)
+      micro->assemble_begin();
       old_sol_u = sol_u;
       old_sol_w = sol_w;
       const auto t1 = std::chrono::steady_clock::now();

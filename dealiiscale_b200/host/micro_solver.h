@@ -134,6 +134,9 @@ class MicroSolver {
     push_macro();
     check(msgpu_assemble(ctx_));
   }
+  // bio: starts the macro-independent part of the next assemble_system() on a second stream, so that it runs beside
+  // the macro solve (msgpu_assemble_begin; a no-op for the other problems and with MSGPU_OVERLAP_ASSEMBLY=0)
+  void assemble_begin() { check(msgpu_assemble_begin(ctx_)); }
   void solve() {
     iterations.assign(num_grids_, 0);
     check(msgpu_solve(ctx_, 1e-12, problem_ == MSGPU_ELLIPTIC ? 1000 : 10000, precond, iterations.data(), nullptr));

@@ -161,6 +161,10 @@ class MicroSolver:
     def assemble_system(self):
         self._check(self.lib.msgpu_assemble(self.h))
 
+    def assemble_begin(self):
+        """bio: the macro-independent part of the next assemble_system() on a second stream (msgpu_assemble_begin)."""
+        self._check(self.lib.msgpu_assemble_begin(self.h))
+
     def solve(self, want_residuals=False):
         its = np.zeros(self.num_grids, dtype=np.int32)
         res = np.zeros(self.num_grids) if want_residuals else None

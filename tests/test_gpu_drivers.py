@@ -269,3 +269,39 @@ def test_stop_test_on_the_device_equals_the_host_aggregation(prm, cells, limit):
     assert out["device"][0] == out["host"][0]
     assert np.array_equal(out["device"][1], out["host"][1]), (out["device"][1], out["host"][1])
     assert np.abs(out["device"][1]).max() > 0
+
+
+@pytest.mark.parametrize("prm,cells,limit", [("biocase.prm", (4, 8), 5), ("biocase-curved.prm", (3, 6), 4)])
+def test_assembly_beside_the_macro_solve_changes_nothing(prm, cells, limit):
+    """msgpu_assemble_begin puts the macro-independent part of the micro assembly (moments, gather) on a second stream
+    while the macro systems are solved; the reference does one after the other (bio manager.cpp:65-68).  Same kernels
+    on the same inputs: every cycle's scalars, macro solutions, flux integrals, micro solutions and CG step counts must
+    EQUAL those of the sequential order (MSGPU_OVERLAP_ASSEMBLY=0)."""
+    lib = _drivers()
+    out = {}
+    for name, env in (("beside", None), ("sequential", "0")):
+        if env:
+            os.environ["MSGPU_OVERLAP_ASSEMBLY"] = env
+        try:
+            h = C.c_void_p(lib.msdrv_bio_create(_path(prm), *cells))
+            assert h.value, lib.msdrv_last_error()
+            n_cycles = lib.msdrv_bio_run(h, limit)
+            N, n = C.c_int(), C.c_int()
+            lib.msdrv_bio_sizes(h, C.byref(N), C.byref(n))
+            N, n = N.value, n.value
+            rec = []
+            for c in range(n_cycles):
+                sc = np.zeros(6)
+                u, w, cu, cw = np.zeros(N), np.zeros(N), np.zeros(N), np.zeros(N)
+                micro, its = np.zeros((N, n)), np.zeros(N, dtype=np.int32)
+                lib.msdrv_bio_history(h, c, dptr(sc), dptr(u), dptr(w), dptr(cu), dptr(cw), dptr(micro), iptr(its))
+                rec.append((sc.copy(), u, w, cu, cw, micro, its))
+            out[name] = rec
+            lib.msdrv_bio_destroy(h)
+        finally:
+            os.environ.pop("MSGPU_OVERLAP_ASSEMBLY", None)
+    assert len(out["beside"]) == len(out["sequential"]) >= 2
+    for a, b in zip(out["beside"], out["sequential"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    assert np.abs(out["beside"][-1][5]).max() > 0
