@@ -186,7 +186,10 @@ int msgpu_create(msgpu_ctx** out, const msgpu_desc* desc) {
     return MSGPU_ERR_CUDA;
   }
   ctx->num_sms = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  // (above the default priority: msgpu_assemble_begin runs its kernels on a second stream of the lowest one)
+  int least_prio = 0, greatest_prio = 0;
+  cudaDeviceGetStreamPriorityRange(&least_prio, &greatest_prio);
+  if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, greatest_prio) != cudaSuccess) {
     delete ctx;
     return MSGPU_ERR_CUDA;
   }
@@ -558,7 +561,11 @@ int msgpu_assemble_begin(msgpu_ctx* ctx) {
     if (rc) return rc;
   }
   if (!ctx->aux_stream) {
-    CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    // lowest priority: the CTAs of the (latency-bound, two-SM) macro solve on the main stream get the slots the
+    // assembly kernels free before those kernels' own next CTAs do
+    int least = 0, greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, least));
     CK(cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming));
   }
