@@ -551,9 +551,8 @@ static int assemble_macro_independent(msgpu_ctx* ctx, cudaStream_t st) {
 
 int msgpu_assemble_begin(msgpu_ctx* ctx) {
   if (!ctx || !ctx->setup_done) return MSGPU_ERR_INVALID;
-  // bio only (the elliptic right-hand side and the parabolic step are one pass each), and not when the assembly is
-  // cached anyway
-  if (ctx->desc.problem != MSGPU_BIO || !ctx->overlap_assembly || ctx->pre_assembly_in_flight) return MSGPU_OK;
+  // elliptic and bio (the parabolic step is one pass of its own), and not when the assembly is cached anyway
+  if (ctx->desc.problem == MSGPU_PARABOLIC || !ctx->overlap_assembly || ctx->pre_assembly_in_flight) return MSGPU_OK;
   if (ctx->reuse_assembly && ctx->assembly_cached) return MSGPU_OK;
   CK(cudaSetDevice(ctx->device));
   if (!ctx->tables_valid) {

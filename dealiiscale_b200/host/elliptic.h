@@ -91,6 +91,7 @@ class MacroSolver {
   void run() {  // macro.cpp:177-181
     if (on_device) {
       compute_microscopic_contribution();  // leaves the integrals on the device; the host copy is for the records
+      micro->assemble_begin();  // matrices, loads and weights of the next micro run: beside the macro solve
       if (micro->solves_macro_here()) {
         last_iterations = micro->macro_solve(1e-12, 1000, true)[0];
         micro->macro_get_solution(0, solution);

@@ -134,7 +134,7 @@ class MicroSolver {
     push_macro();
     check(msgpu_assemble(ctx_));
   }
-  // bio: starts the macro-independent part of the next assemble_system() on a second stream, so that it runs beside
+  // elliptic, bio: starts the macro-independent part of the next assemble_system() on a second stream, so that it runs beside
   // the macro solve (msgpu_assemble_begin; a no-op for the other problems and with MSGPU_OVERLAP_ASSEMBLY=0)
   void assemble_begin() { check(msgpu_assemble_begin(ctx_)); }
   void solve() {

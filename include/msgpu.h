@@ -124,12 +124,12 @@ int msgpu_set_macro_solution(msgpu_ctx* ctx, const double* u, const double* w);
  * (bio micro.cpp:183-298).  Kernels: line tables -> cell moments -> stencil gather (+ faces,
  * + Dirichlet elimination).  Matrices, right-hand sides and start vectors stay on the device. */
 int msgpu_assemble(msgpu_ctx* ctx);
-/* Optional, bio: starts the part of msgpu_assemble that does not depend on the macro solution (cell and face moments,
+/* Optional, elliptic and bio: starts the part of msgpu_assemble that does not depend on the macro solution (cell and face moments,
  * the gather into matrices / loads / weights) on a second stream and returns at once; the next msgpu_assemble joins it
  * and only adds the macro-dependent right-hand sides.  Lets a host run MacroSolver::assemble_system + solve
- * (bio macro.cpp:100-202; msgpu_macro_solve) beside it - the reference does the two one after the other
- * (bio manager.cpp:65-68), the results are the same bits.  Call it after the msgpu_coupling / stop-test calls of the
- * cycle before; a no-op for the other problems, with MSGPU_OVERLAP_ASSEMBLY=0 and while MSGPU_REUSE_ASSEMBLY=1 has the
+ * (macro.cpp:57-114, bio macro.cpp:100-202; msgpu_macro_solve) beside it - the reference does the two one after the
+ * other (manager.cpp:53-58, bio manager.cpp:65-68), the results are the same bits.  Call it after the msgpu_coupling / stop-test calls of the
+ * cycle before; a no-op for the parabolic problem, with MSGPU_OVERLAP_ASSEMBLY=0 and while MSGPU_REUSE_ASSEMBLY=1 has the
  * assembly cached. */
 int msgpu_assemble_begin(msgpu_ctx* ctx);
 
