@@ -138,3 +138,65 @@ def test_full_size_properties_biocase_6_6():
     assert np.linalg.norm(A @ sols[1][4] - b) < 1e-10      # the assembled system is the one that was solved
     assert np.allclose(A, A.T, rtol=0, atol=0)
     ms.close()
+
+
+def test_assemble_begin_in_every_order():
+    """msgpu_assemble_begin (include/msgpu.h) is optional and must be harmless wherever a host calls it: twice in a
+    row, before inputs change (new scalars / a new set-up retire what is in flight), right before destruction, for the
+    elliptic problem, and never for results: the solutions equal those of a plain assemble + solve bit for bit."""
+    from dealiiscale_b200 import capi
+    from dealiiscale_b200.micro import MicroSolver
+    from dealiiscale_b200.prm import BioData, EllipticData
+
+    g = np.linspace(-0.8, 0.9, 4)
+    xy = np.array([(a, b) for b in g for a in g])
+    u, w = 1.0 + 0.5 * xy[:, 0], 0.25 - xy[:, 1]
+
+    def plain(scalars=None):
+        ms = _bio("biocase-b.prm", 12, xy)
+        if scalars is not None:
+            ms.set_scalars(scalars)
+        ms.set_macro_solution(u, w)
+        its = ms.run()
+        x, c = ms.solutions(), ms.coupling()
+        ms.close()
+        return x, its.copy(), c
+
+    x0, its0, c0 = plain()
+    ms = _bio("biocase-b.prm", 12, xy)
+    ms.assemble_begin()
+    ms.assemble_begin()                      # second call: nothing to add
+    ms.set_macro_solution(u, w)
+    its = ms.run()                           # joins what is in flight
+    assert np.array_equal(ms.solutions(), x0) and np.array_equal(its, its0)
+    cu, cw = ms.coupling()
+    assert np.array_equal(cu, c0[0]) and np.array_equal(cw, c0[1])
+    # new Robin coefficients while an assembly is in flight: it is retired, the next one sees the new values
+    sc = list(BioData(os.path.join(INPUT, "biocase-b.prm")).scalars())  # kappa_1 .. kappa_4, D_2
+    sc[1] *= 2.0
+    sc[3] *= 0.5
+    ms.assemble_begin()
+    ms.set_scalars(sc)
+    ms.zero_solutions()
+    its = ms.run()
+    x1, its1, _ = plain(sc)
+    assert np.array_equal(ms.solutions(), x1) and np.array_equal(its, its1)
+    assert not np.array_equal(x1, x0)
+    ms.assemble_begin()
+    ms.close()                               # destroyed with an assembly in flight
+
+    o = OracleElliptic("elliptic_non_linear.prm", 1, 3)
+    xe = o.grid_locations()
+    ue = np.sin(xe[:, 0]) * xe[:, 1] + 0.3
+    o.micro_run(ue)
+    me = MicroSolver(capi.ELLIPTIC, EllipticData(os.path.join(INPUT, "elliptic_non_linear.prm")), 8)
+    me.set_grid_locations(xe)
+    me.setup()
+    me.assemble_begin()
+    me.set_macro_solution(ue)
+    me.run()
+    xs = me.solutions()
+    for k in range(o.N):
+        assert rel_l2(xs[k], o.solution(k)) < 1e-10
+    me.close()
+    o.close()
