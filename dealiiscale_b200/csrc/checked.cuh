@@ -6,8 +6,8 @@
 // halos, guard zones, per-warp column blocks).  In a checked build every shared-memory access of those kernels goes
 // through CheckedPtr, which knows the window it may touch, and every tensor-memory address is compared with the
 // column block the warp owns; a violation reports its source line through the device-side assert and fails the launch.  In the product build
-// CheckedPtr<T> is T* and the checks expand to nothing (identical SASS: tests/test_checked_build.py compares the
-// register counts).
+// CheckedPtr<T> is T* and the checks expand to nothing (tests/test_checked_build.py: no assert message in libmsgpu.so,
+// register budgets of the kernels as the launch code expects them).
 #pragma once
 #include <cassert>
 #include <cstdint>
