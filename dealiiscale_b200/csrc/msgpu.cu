@@ -572,11 +572,22 @@ int msgpu_assemble_begin(msgpu_ctx* ctx) {
   // rewritten now), beside whatever it is given next
   CK(cudaEventRecord(ctx->ev_main, ctx->stream));
   CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_main, 0));
-  const int rc = assemble_macro_independent(ctx, ctx->aux_stream);
-  if (rc) return rc;
-  CKVM();
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(ctx->ev_pre, ctx->aux_stream));
+  int rc = assemble_macro_independent(ctx, ctx->aux_stream);
+  if (rc == MSGPU_OK) {
+    if (const char* e = vm_launch_error()) {  // a launcher refused an interpreter kernel
+      ctx->err = e;
+      vm_clear_launch_error();
+      rc = MSGPU_ERR_UNSUPPORTED;
+    } else if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ctx->ev_pre, ctx->aux_stream) != cudaSuccess) {
+      ctx->err = "msgpu_assemble_begin: launch on the auxiliary stream failed";
+      rc = MSGPU_ERR_CUDA;
+    }
+  }
+  if (rc != MSGPU_OK) {
+    // whatever did get launched must not run beside the full assembly the caller falls back to
+    cudaStreamSynchronize(ctx->aux_stream);
+    return rc;
+  }
   ctx->pre_assembly_in_flight = 1;
   return MSGPU_OK;
 }
