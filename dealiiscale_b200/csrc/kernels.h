@@ -157,6 +157,7 @@ struct CgArgs {
   // (F constant per system: every bio set, the linear elliptic maps, the parabolic driver) has only nine
   // distinct matrix rows - one per position class {first, inner, last}^2 - so the CG kernel keeps the stencil
   // in registers instead of the matrix in tensor memory, and two systems share an SM.
+  const double* x_in = nullptr;  // class-compressed kernel only: start vectors read from here instead of x (null: x)
   double* stencil_ws = nullptr;  // [N or 1][STENCIL_TABLE] class tables, written by the compression kernel; null: off
   int* stencil_bad = nullptr;    // device int, raised when some system is NOT class-uniform
   int stencil_hint = 0;          // 0 unknown: compress + verify, both kernels launched behind the gate;

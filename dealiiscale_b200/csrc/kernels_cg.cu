@@ -1565,6 +1565,8 @@ int launch_cg(cudaStream_t s, const CgArgs& a_in, int num_sms, int* variant) {
       a.gate_run_if_zero = 0;
     }
   }
+  if (a.x_in != nullptr && a.x_in != a.x)  // the general kernels solve in place: bring the start vectors over
+    cudaMemcpyAsync(a.x, a.x_in, sizeof(double) * static_cast<size_t>(a.N) * a.md.n, cudaMemcpyDeviceToDevice, s);
   int general_variant = 0;
   const int r = launch_cg_general(s, a, num_sms, &general_variant, sw);
   if (r < 0) return r;

@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
         if (nx < a.N) {
           const uint32_t row_bytes = static_cast<uint32_t>(n) * 8u & ~15u;
           l2_prefetch_bulk(a.b + static_cast<size_t>(nx) * n, row_bytes);
-          l2_prefetch_bulk(a.x + static_cast<size_t>(nx) * n, row_bytes);
+          l2_prefetch_bulk((a.x_in ? a.x_in : a.x) + static_cast<size_t>(nx) * n, row_bytes);
         }
       }
     }
@@ -381,9 +381,10 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, TM ? 2 : 1)
     if (k >= a.N) break;
     const double* bk = a.b + static_cast<size_t>(k) * n;
     double* xk = a.x + static_cast<size_t>(k) * n;
+    const double* xin = (a.x_in ? a.x_in : a.x) + static_cast<size_t>(k) * n;  // start vector (msgpu_solve, bio)
     if (tid < STENCIL_TABLE)
       tab[tid] = __ldg(a.stencil_ws + (a.diag_stride != 0 ? static_cast<size_t>(k) * STENCIL_TABLE : 0) + tid);
-    stage_in(xk);
+    stage_in(xin);
     __syncthreads();
     // couplings of this tile from the class table T[cx][cy][e] (form checked by k_stencil_compress)
     {

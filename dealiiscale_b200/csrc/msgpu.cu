@@ -652,8 +652,19 @@ int msgpu_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int precond, int* it
   CK(cudaSetDevice(ctx->device));
   const MeshDims& md = ctx->md;
   const bool shared_matrix = ctx->desc.problem == MSGPU_PARABOLIC;
-  if (ctx->desc.problem == MSGPU_BIO)  // old_solutions = solutions (bio micro.cpp:300)
-    CK(cudaMemcpyAsync(ctx->d_xold, ctx->d_x, sizeof(double) * ctx->N * md.n, cudaMemcpyDeviceToDevice, ctx->stream));
+  // old_solutions = solutions (bio micro.cpp:300).  When the class-compressed kernel is known to do the solve it reads
+  // its start vectors from one buffer and writes the solutions to the other: the two buffers change roles instead of
+  // 2 x 143 MB being copied at `6 6`.
+  bool swapped_in = false;
+  if (ctx->desc.problem == MSGPU_BIO) {
+    if (ctx->stencil_hint == 1 && precond == MSGPU_PRECOND_IDENTITY && ctx->cg_sw.stencil &&
+        stencil_supported(md, 0)) {
+      std::swap(ctx->d_x, ctx->d_xold);
+      swapped_in = true;
+    } else {
+      CK(cudaMemcpyAsync(ctx->d_xold, ctx->d_x, sizeof(double) * ctx->N * md.n, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
   {
     PhaseTimer pt(ctx, PH_CG);
     CgArgs a;
@@ -663,6 +674,7 @@ int msgpu_solve(msgpu_ctx* ctx, double abs_tol, int max_it, int precond, int* it
     a.diag_stride = shared_matrix ? 0 : static_cast<long long>(NDIAG) * md.ld;
     a.b = ctx->d_b;
     a.x = ctx->d_x;
+    a.x_in = swapped_in ? ctx->d_xold : nullptr;
     a.tol = abs_tol;
     a.max_it = max_it;
     a.precond = precond;
