@@ -501,12 +501,16 @@ MSGPU_HOSTDEV bool on_boundary(int ix, int iy, int m) {
 // MatrixTools::apply_boundary_values (micro.cpp:168): boundary row d keeps its diagonal a_dd,
 // b_d = v_d a_dd, x_d = v_d; every row r coupled to d gets b_r -= a_rd / a_dd * (v_d a_dd).
 // The couplings themselves are zeroed by k_mask_dirichlet afterwards.
+// (system k, node r: the kernels run on a (system, node-block) grid, the CPU harness walks through global indices)
+MSGPU_HOSTDEV void body_rhs_node(const RhsArgs& a, int k, int r);
 MSGPU_HOSTDEV void body_rhs(const RhsArgs& a, long long gtid) {
   const MeshDims& md = a.md;
-  const long long t = gtid;
-  if (t >= static_cast<long long>(a.N) * md.n) return;
-  const int k = static_cast<int>(t / md.n), r = static_cast<int>(t % md.n);
-  const int ix = r / md.m, iy = r % md.m;
+  if (gtid >= static_cast<long long>(a.N) * md.n) return;
+  body_rhs_node(a, static_cast<int>(gtid / md.n), static_cast<int>(gtid % md.n));
+}
+MSGPU_HOSTDEV void body_rhs_node(const RhsArgs& a, int k, int r) {
+  const MeshDims& md = a.md;
+  const int ix = r / md.m, iy = r - ix * md.m;
   const size_t vo = static_cast<size_t>(k) * md.n;
   double val = a.b0[vo + r];
   if (a.problem == PF_ELLIPTIC) {
@@ -558,11 +562,13 @@ MSGPU_HOSTDEV void body_rhs(const RhsArgs& a, long long gtid) {
   a.b[vo + r] = val;
 }
 
+MSGPU_HOSTDEV void body_mask_dirichlet_node(const MeshDims& md, double* __restrict__ diag, int k, int r);
 MSGPU_HOSTDEV void body_mask_dirichlet(const MeshDims& md, int N, double* __restrict__ diag, long long gtid) {
-  const long long t = gtid;
-  if (t >= static_cast<long long>(N) * md.n) return;
-  const int k = static_cast<int>(t / md.n), r = static_cast<int>(t % md.n);
-  const int ix = r / md.m, iy = r % md.m;
+  if (gtid >= static_cast<long long>(N) * md.n) return;
+  body_mask_dirichlet_node(md, diag, static_cast<int>(gtid / md.n), static_cast<int>(gtid % md.n));
+}
+MSGPU_HOSTDEV void body_mask_dirichlet_node(const MeshDims& md, double* __restrict__ diag, int k, int r) {
+  const int ix = r / md.m, iy = r - ix * md.m;
   double* dg = diag + static_cast<size_t>(k) * NDIAG * md.ld;
   const int ddx[4] = {0, 1, 1, 1}, ddy[4] = {1, -1, 0, 1};
   const bool me = on_boundary(ix, iy, md.m);

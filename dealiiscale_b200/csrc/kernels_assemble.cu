@@ -156,10 +156,12 @@ __global__ void __launch_bounds__(TB) k_boundary_values(const __grid_constant__ 
                        TB);
 }
 __global__ void __launch_bounds__(TB) k_rhs(RhsArgs a) {
-  body_rhs(a, static_cast<long long>(blockIdx.x) * TB + threadIdx.x);
+  const int r = static_cast<int>(blockIdx.y) * TB + static_cast<int>(threadIdx.x);
+  if (r < a.md.n) body_rhs_node(a, static_cast<int>(blockIdx.x), r);
 }
 __global__ void __launch_bounds__(TB) k_mask_dirichlet(MeshDims md, int N, double* __restrict__ diag) {
-  body_mask_dirichlet(md, N, diag, static_cast<long long>(blockIdx.x) * TB + threadIdx.x);
+  const int r = static_cast<int>(blockIdx.y) * TB + static_cast<int>(threadIdx.x);
+  if (r < md.n && static_cast<int>(blockIdx.x) < N) body_mask_dirichlet_node(md, diag, static_cast<int>(blockIdx.x), r);
 }
 
 thread_local char g_vm_error[256] = {0};
@@ -288,7 +290,7 @@ int launch_boundary_values(cudaStream_t s, const VmProgram& prog, MeshDims md, T
 
 int launch_rhs_and_dirichlet(cudaStream_t s, const RhsArgs& a) {
   if (a.N == 0) return 0;
-  const int blocks = blocks_for(static_cast<long long>(a.N) * a.md.n);
+  const dim3 blocks(static_cast<unsigned>(a.N), static_cast<unsigned>((a.md.n + TB - 1) / TB));  // (system, node block)
   k_rhs<<<blocks, TB, 0, s>>>(a);
   if (a.problem == PF_ELLIPTIC) {
     k_mask_dirichlet<<<blocks, TB, 0, s>>>(a.md, a.N, a.diag);

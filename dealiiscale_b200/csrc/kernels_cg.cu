@@ -1296,9 +1296,10 @@ __global__ void __launch_bounds__(128) k_coupling(CouplingArgs a) {
 
 __global__ void __launch_bounds__(128) k_shared_spmv(MeshDims md, int N, const double* __restrict__ dg,
                                                       const double* __restrict__ x, double* __restrict__ y) {
-  const long long t = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
-  if (t >= static_cast<long long>(N) * md.n) return;
-  const int k = static_cast<int>(t / md.n), r = static_cast<int>(t % md.n);
+  // blockIdx.x: system, blockIdx.y: block of 128 nodes
+  const int k = static_cast<int>(blockIdx.x), r = static_cast<int>(blockIdx.y) * 128 + static_cast<int>(threadIdx.x);
+  if (k >= N || r >= md.n) return;
+  const size_t t = static_cast<size_t>(k) * md.n + r;
   const double* v = x + static_cast<size_t>(k) * md.n;
   const int off[4] = {1, md.m - 1, md.m, md.m + 1};
   double s = dg[r] * v[r];
@@ -1583,8 +1584,8 @@ int launch_coupling(cudaStream_t s, const CouplingArgs& a) {
 
 int launch_shared_spmv(cudaStream_t s, MeshDims md, int N, const double* diag, const double* x, double* y) {
   if (N == 0) return 0;
-  const long long work = static_cast<long long>(N) * md.n;
-  k_shared_spmv<<<static_cast<int>((work + 127) / 128), 128, 0, s>>>(md, N, diag, x, y);
+  const dim3 grid(static_cast<unsigned>(N), static_cast<unsigned>((md.n + 127) / 128));
+  k_shared_spmv<<<grid, 128, 0, s>>>(md, N, diag, x, y);
   return 1;
 }
 
